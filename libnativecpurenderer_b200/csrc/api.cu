@@ -1,0 +1,1208 @@
+// Host runtime + C ABI of the B200-native libNativeCPURenderer.so.
+//
+//   * contexts own an HBM-resident f64 canvas [h][w][ipp], a CUDA stream and a command recorder;
+//   * textures are uploaded once and stay in HBM (RGBA8/RGB8 when born from bytes, f64 otherwise);
+//   * state calls (transform / colour stacks) run on the host with the reference's expression trees;
+//   * draw calls append one NcrCmd to pinned staging; any canvas read flushes: one H2D copy of the batch,
+//     ncr_bin_coarse -> ncr_bin_fine -> ncr_composite on the context's stream, optional fused u8 image.
+//
+// There is no CPU rendering path in this library: without a usable CUDA device CreateRenderContext and the
+// texture constructors print the reason, record it for NcrLastError() and return NULL.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <atomic>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "../../include/ncr_b200.h"
+#include "hiteffect.h"
+#include "kernels.h"
+#include "ncr_cmd.h"
+#include "ncr_trace.h"
+#include "state.h"
+
+// ------------------------------------------------------------------------------------------------
+// device bookkeeping
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+std::mutex g_mu;
+int g_dev = -1;
+int g_init = 0;   // 0 untried, 1 ok, -1 failed
+char g_err[512] = "";
+char g_devname[256] = "";
+std::atomic<unsigned long long> g_launches{0};
+void* g_l2_scrub = nullptr;
+const size_t kL2ScrubBytes = 256u << 20;
+
+void set_error(const char* what, const char* detail) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, detail);
+    fprintf(stderr, "[libNativeCPURenderer/b200] %s\n", g_err);
+}
+
+bool ck(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    set_error(what, cudaGetErrorString(e));
+    return false;
+}
+#define CK(call) ck((call), #call)
+
+// Selects the device once (NCR_DEVICE, else LOCAL_RANK, else 0) and makes it current on the calling thread.
+bool use_device() {
+    if (g_init == 1) return cudaSetDevice(g_dev) == cudaSuccess;
+    if (g_init == -1) return false;
+    int want = 0;
+    const char* env = getenv("NCR_DEVICE");
+    if (!env || !*env) env = getenv("LOCAL_RANK");
+    if (env && *env) want = atoi(env);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("no usable CUDA device (this library has no CPU rendering path)",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        g_init = -1;
+        return false;
+    }
+    if (want < 0 || want >= count) want = want % count;
+    if (!CK(cudaSetDevice(want))) { g_init = -1; return false; }
+    cudaDeviceProp prop;
+    if (!CK(cudaGetDeviceProperties(&prop, want))) { g_init = -1; return false; }
+    if (prop.major < 10) {
+        char msg[160];
+        snprintf(msg, sizeof(msg), "%s is sm_%d%d; the kernels are built for sm_100a only", prop.name, prop.major, prop.minor);
+        set_error("unsupported device", msg);
+        g_init = -1;
+        return false;
+    }
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        snprintf(g_devname, sizeof(g_devname), "%s", prop.name);
+    }
+    g_dev = want;
+    g_init = 1;
+    return true;
+}
+
+struct DevMem {
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~DevMem() {
+        if (p) cudaFree(p);
+    }
+};
+typedef std::shared_ptr<DevMem> DevRef;
+
+DevRef dev_alloc(size_t bytes) {
+    DevRef m = std::make_shared<DevMem>();
+    if (!CK(cudaMalloc(&m->p, bytes ? bytes : 16))) return nullptr;
+    m->bytes = bytes;
+    return m;
+}
+
+template <class T>
+struct DevVec {
+    T* p = nullptr;
+    size_t cap = 0;
+    bool reserve(size_t n) {
+        if (n <= cap) return true;
+        size_t want = cap ? cap : 1024;
+        while (want < n) want *= 2;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        if (!CK(cudaMalloc((void**)&p, want * sizeof(T)))) return false;
+        cap = want;
+        return true;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+template <class T>
+struct PinnedVec {
+    T* p = nullptr;
+    size_t cap = 0;
+    bool reserve(size_t n, size_t keep) {
+        if (n <= cap) return true;
+        size_t want = cap ? cap : 4096;
+        while (want < n) want *= 2;
+        T* q = nullptr;
+        if (!CK(cudaMallocHost((void**)&q, want * sizeof(T)))) return false;
+        if (p) {
+            memcpy(q, p, keep * sizeof(T));
+            cudaFreeHost(p);
+        }
+        p = q;
+        cap = want;
+        return true;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+const uint32_t kMagicCtx = 0x4e435243u;   // "NCRC"
+const uint32_t kMagicTex = 0x4e435254u;   // "NCRT"
+
+}   // namespace
+
+struct NcrTexture {
+    uint32_t magic = kMagicTex;
+    bool dead = false;
+    i64 w = 0, h = 0;
+    bool alpha = false;
+    bool is_f64 = false;
+    DevRef buf;                     // texels; null for an alias
+    NcrContext* alias = nullptr;    // CreateTextureFromRenderContextShared: the canvas itself (cpp:382)
+    std::vector<unsigned char> shadow;   // host copy of u8 texels, fetched on demand (hit-effect masks)
+};
+
+struct NcrStaging {
+    PinnedVec<NcrCmd> cmds;
+    PinnedVec<NcrBox> boxes;
+    PinnedVec<double> aux;
+    cudaEvent_t done = nullptr;
+    bool inflight = false;
+};
+
+struct NcrContext {
+    uint32_t magic = kMagicCtx;
+    bool dead = false;
+    i64 w = 0, h = 0;
+    bool alpha = false;
+    DevRef fb;
+    NcrState st;
+    std::vector<NcrState> stack;
+
+    // recorder
+    NcrStaging stg[2];
+    int cur = 0;
+    size_t n = 0, n_aux = 0;
+    unsigned long long coarse_need = 0, fine_need = 0;
+    bool load_fb = true;
+    std::vector<DevRef> refs, last_refs;
+
+    // device side
+    DevVec<NcrCmd> d_cmds;
+    DevVec<NcrBox> d_boxes;
+    DevVec<double> d_aux;
+    DevVec<uint32_t> d_coarse, d_coarse_off, d_fine, d_fine_off, d_cursors;
+    DevVec<unsigned char> d_u8;
+    bool u8_valid = false;
+    uint32_t* h_cursors = nullptr;   // pinned, 8 words
+    bool cursors_pending = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    bool ev_pending = false;
+    NcrFlushArgs last;
+    bool has_last = false;
+    int stats_mode = 0;
+    NcrStats stats;
+    bool failed = false;   // sticky device error
+
+    // extensions
+    bool clip_on = false;
+    i64 clip_l = 0, clip_r = 0, clip_t = 0, clip_b = 0;
+    int sampling = 0;
+};
+
+namespace {
+
+inline NcrContext* live(RenderContext* c) {
+    if (!c || c->magic != kMagicCtx || c->dead) return nullptr;
+    return c;
+}
+inline NcrTexture* live(Texture* t) {
+    if (!t || t->magic != kMagicTex || t->dead) return nullptr;
+    return t;
+}
+inline int ipp_of(const NcrContext* c) { return c->alpha ? 4 : 3; }
+
+void frame_dims(const NcrContext* c, NcrFrameDims* d) {
+    d->w = (int32_t)c->w;
+    d->h = (int32_t)c->h;
+    d->ipp = ipp_of(c);
+    d->tiles_x = (int32_t)((c->w + NCR_TILE - 1) / NCR_TILE);
+    d->tiles_y = (int32_t)((c->h + NCR_TILE - 1) / NCR_TILE);
+    d->bins_x = (d->tiles_x + NCR_COARSE - 1) / NCR_COARSE;
+    d->bins_y = (d->tiles_y + NCR_COARSE - 1) / NCR_COARSE;
+}
+
+bool alloc_canvas(NcrContext* c, i64 w, i64 h) {
+    if (w < 0 || h < 0 || w > 0x3fffffff || h > 0x3fffffff) {
+        set_error("canvas size", "out of range");
+        return false;
+    }
+    const size_t bytes = (size_t)w * (size_t)h * (c->alpha ? 4 : 3) * sizeof(double);
+    DevRef fb = dev_alloc(bytes);
+    if (!fb) return false;
+    // The reference leaves new canvases uninitialised (cpp:15); the product defines them as zero.
+    if (!CK(cudaMemsetAsync(fb->p, 0, bytes ? bytes : 16, c->stream))) return false;
+    c->fb = fb;
+    c->w = w;
+    c->h = h;
+    c->u8_valid = false;
+    c->has_last = false;
+    return true;
+}
+
+// Collects the results of the previous flush (list sizes, pixel counter, overflow flag, event timings).
+void harvest(NcrContext* c) {
+    if (c->cursors_pending) {
+        c->cursors_pending = false;
+        c->stats.coarse_entries = c->h_cursors[0];
+        c->stats.fine_entries = c->h_cursors[1];
+        c->stats.blended_pixels = (unsigned long long)c->h_cursors[2] | ((unsigned long long)c->h_cursors[3] << 32);
+        if (c->h_cursors[4]) {
+            set_error("tile-list overflow", c->h_cursors[4] == 1 ? "coarse list" : "fine list");
+            c->failed = true;
+        }
+    }
+    if (c->ev_pending) {
+        c->ev_pending = false;
+        cudaEventElapsedTime(&c->stats.ms_bin_coarse, c->ev[0], c->ev[1]);
+        cudaEventElapsedTime(&c->stats.ms_bin_fine, c->ev[1], c->ev[2]);
+        cudaEventElapsedTime(&c->stats.ms_composite, c->ev[2], c->ev[3]);
+        cudaEventElapsedTime(&c->stats.ms_total, c->ev[0], c->ev[3]);
+    }
+}
+
+bool sync_ctx(NcrContext* c) {
+    if (!CK(cudaStreamSynchronize(c->stream))) {
+        c->failed = true;
+        return false;
+    }
+    for (int k = 0; k < 2; ++k) c->stg[k].inflight = false;
+    harvest(c);
+    return !c->failed;
+}
+
+// Submits the recorded batch.  want_u8: also produce the (iu8)(v*255) image in d_u8 (fused into the composite).
+bool flush(NcrContext* c, bool want_u8) {
+    if (!use_device()) return false;
+    const size_t n_elems = (size_t)c->w * c->h * ipp_of(c);
+    if (c->n == 0) {
+        if (want_u8 && !c->u8_valid && n_elems) {
+            if (!c->d_u8.reserve(n_elems)) return false;
+            ncr_launch_convert_u8((const double*)c->fb->p, c->d_u8.p, n_elems, c->stream);
+            g_launches += 1;
+            c->stats.kernel_launches += 1;
+            c->u8_valid = true;
+        }
+        return true;
+    }
+    if (c->cursors_pending || c->ev_pending) {
+        // results of the previous flush live in pinned words that the next one overwrites
+        if (!sync_ctx(c)) return false;
+    }
+    NcrFlushArgs A;
+    memset(&A, 0, sizeof(A));
+    frame_dims(c, &A.d);
+    const size_t n_tiles = (size_t)A.d.tiles_x * A.d.tiles_y, n_bins = (size_t)A.d.bins_x * A.d.bins_y;
+    NcrStaging& S = c->stg[c->cur];
+    bool ok = c->d_cmds.reserve(c->n) && c->d_boxes.reserve(c->n) && c->d_aux.reserve(c->n_aux + 2) &&
+              c->d_coarse.reserve(c->coarse_need + 1) && c->d_coarse_off.reserve(2 * n_bins) &&
+              c->d_fine.reserve(c->fine_need + 1) && c->d_fine_off.reserve(2 * n_tiles) && c->d_cursors.reserve(8);
+    if (ok && want_u8) ok = c->d_u8.reserve(n_elems);
+    if (!ok) { c->failed = true; return false; }
+    ok = CK(cudaMemcpyAsync(c->d_cmds.p, S.cmds.p, c->n * sizeof(NcrCmd), cudaMemcpyHostToDevice, c->stream)) &&
+         CK(cudaMemcpyAsync(c->d_boxes.p, S.boxes.p, c->n * sizeof(NcrBox), cudaMemcpyHostToDevice, c->stream));
+    if (ok && c->n_aux)
+        ok = CK(cudaMemcpyAsync(c->d_aux.p, S.aux.p, c->n_aux * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (!ok) { c->failed = true; return false; }
+    cudaEventRecord(S.done, c->stream);
+    S.inflight = true;
+    c->stats.h2d_bytes += c->n * (sizeof(NcrCmd) + sizeof(NcrBox)) + c->n_aux * sizeof(double);
+
+    A.fb = (double*)c->fb->p;
+    A.u8_out = want_u8 ? c->d_u8.p : nullptr;
+    A.cmds = c->d_cmds.p;
+    A.boxes = c->d_boxes.p;
+    A.aux = c->d_aux.p;
+    A.n_cmds = (uint32_t)c->n;
+    A.load_fb = c->load_fb ? 1u : 0u;
+    A.coarse_list = c->d_coarse.p;
+    A.coarse_off = c->d_coarse_off.p;
+    A.fine_list = c->d_fine.p;
+    A.fine_off = c->d_fine_off.p;
+    A.cursors = c->d_cursors.p;
+    A.coarse_cap = (uint32_t)c->d_coarse.cap;
+    A.fine_cap = (uint32_t)c->d_fine.cap;
+    A.count_pixels = (c->stats_mode & 1) ? 1u : 0u;
+    const bool timed = (c->stats_mode & 2) != 0;
+    ncr_launch_flush(&A, c->stream, timed ? c->ev : nullptr);
+    g_launches += 3;
+    c->stats.kernel_launches += 3;
+    c->ev_pending = timed;
+    cudaMemcpyAsync(c->h_cursors, c->d_cursors.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+    c->cursors_pending = true;
+    if (!CK(cudaGetLastError())) { c->failed = true; return false; }
+
+    c->stats.n_cmds = c->n;
+    c->stats.flushes += 1;
+    c->last = A;
+    c->has_last = true;
+    c->last_refs.swap(c->refs);
+    c->refs.clear();
+    c->n = 0;
+    c->n_aux = 0;
+    c->coarse_need = c->fine_need = 0;
+    c->load_fb = true;
+    c->u8_valid = want_u8;
+    c->cur ^= 1;
+    return true;
+}
+
+// Room for one more command (+ extra aux doubles) in the current staging buffers.
+bool reserve_cmd(NcrContext* c, size_t extra_aux) {
+    NcrStaging& S = c->stg[c->cur];
+    if (S.inflight) {
+        cudaEventSynchronize(S.done);
+        S.inflight = false;
+    }
+    if (c->n + 1 > S.cmds.cap) {
+        if (!S.cmds.reserve(c->n + 1, c->n) || !S.boxes.reserve(S.cmds.cap, c->n)) return false;
+    }
+    if (c->n_aux + extra_aux > S.aux.cap) {
+        if (!S.aux.reserve(c->n_aux + extra_aux, c->n_aux)) return false;
+    }
+    return true;
+}
+
+const unsigned long long kMaxPendingEntries = 48ull << 20;   // tile-list entries (4 B each) before an early submit
+const size_t kMaxPendingCmds = 1u << 20;
+
+// Starts a command covering the pixel box [l,r) x [t,b) (already clamped to the canvas).  Returns nullptr when
+// the box is empty — no pixel can be touched, so nothing is recorded.
+NcrCmd* begin_cmd(NcrContext* c, uint32_t op, i64 l, i64 r, i64 t, i64 b, bool clip = true, size_t extra_aux = 0) {
+    if (c->failed) return nullptr;
+    uint32_t flags = 0;
+    if (clip && c->clip_on) {
+        l = std::max(l, c->clip_l); r = std::min(r, c->clip_r);
+        t = std::max(t, c->clip_t); b = std::min(b, c->clip_b);
+        flags |= NCR_F_CLIP;
+    }
+    if (l >= r || t >= b) return nullptr;
+    if (c->n >= kMaxPendingCmds || c->fine_need > kMaxPendingEntries) {
+        if (!flush(c, false)) return nullptr;
+    }
+    if (!reserve_cmd(c, extra_aux)) { c->failed = true; return nullptr; }
+    NcrStaging& S = c->stg[c->cur];
+    NcrCmd* cmd = &S.cmds.p[c->n];
+    memset(cmd, 0, sizeof(NcrCmd));
+    cmd->op = op;
+    cmd->flags = flags;
+    cmd->l = (int32_t)l; cmd->r = (int32_t)r; cmd->t = (int32_t)t; cmd->b = (int32_t)b;
+    for (int k = 0; k < 4; ++k) cmd->ct[k] = c->st.ct[k];
+    NcrBox& bx = S.boxes.p[c->n];
+    bx.l = cmd->l; bx.r = cmd->r; bx.t = cmd->t; bx.b = cmd->b;
+    const unsigned long long tx = ((r - 1) / NCR_TILE) - (l / NCR_TILE) + 1, ty = ((b - 1) / NCR_TILE) - (t / NCR_TILE) + 1;
+    const i64 edge = NCR_TILE * NCR_COARSE;
+    const unsigned long long bxn = ((r - 1) / edge) - (l / edge) + 1, byn = ((b - 1) / edge) - (t / edge) + 1;
+    c->fine_need += tx * ty;
+    c->coarse_need += bxn * byn;
+    c->n += 1;
+    return cmd;
+}
+
+void put_inverse(NcrContext* c, NcrCmd* cmd) { ncr_inverse(c->st.m, cmd->inv); }
+
+// Texture operand of a draw.  Aliases of a canvas (cpp:377-384) are resolved to a snapshot of that canvas as of
+// this call, which is what an immediate-mode read of the shared buffer would have seen.
+bool bind_texture(NcrTexture* tex, const void** ptr, uint32_t* flags, DevRef* keep) {
+    if (tex->alias) {
+        NcrContext* src = live(tex->alias);
+        if (!src) return false;
+        if (!flush(src, false) || !sync_ctx(src)) return false;
+        const size_t bytes = (size_t)src->w * src->h * ipp_of(src) * sizeof(double);
+        DevRef snap = dev_alloc(bytes);
+        if (!snap) return false;
+        if (!CK(cudaMemcpy(snap->p, src->fb->p, bytes, cudaMemcpyDeviceToDevice))) return false;
+        *ptr = snap->p;
+        *keep = snap;
+        *flags = NCR_F_TEX_F64 | (src->alpha ? NCR_F_TEX_ALPHA : 0);
+        return true;
+    }
+    *ptr = tex->buf->p;
+    *keep = tex->buf;
+    *flags = (tex->is_f64 ? NCR_F_TEX_F64 : 0) | (tex->alpha ? NCR_F_TEX_ALPHA : 0);
+    return true;
+}
+
+void tex_dims(NcrTexture* tex, i64* w, i64* h) {
+    if (tex->alias && live(tex->alias)) {
+        *w = tex->alias->w;
+        *h = tex->alias->h;
+    } else {
+        *w = tex->w;
+        *h = tex->h;
+    }
+}
+
+void keep_ref(NcrContext* c, const DevRef& r) {
+    if (c->refs.empty() || c->refs.back() != r) c->refs.push_back(r);
+}
+
+NcrTexture* new_texture(i64 w, i64 h, bool alpha, bool is_f64, const void* host_data) {
+    if (!use_device()) return nullptr;
+    if (w < 0 || h < 0) { set_error("texture size", "negative"); return nullptr; }
+    const size_t bytes = (size_t)w * h * (alpha ? 4 : 3) * (is_f64 ? 8 : 1);
+    DevRef buf = dev_alloc(bytes);
+    if (!buf) return nullptr;
+    if (host_data && bytes && !CK(cudaMemcpy(buf->p, host_data, bytes, cudaMemcpyHostToDevice))) return nullptr;
+    NcrTexture* t = new NcrTexture();
+    t->w = w; t->h = h; t->alpha = alpha; t->is_f64 = is_f64;
+    t->buf = buf;
+    return t;
+}
+
+// Materialises a texture operand for setup-time consumers (resample, hit-effect mask): alias -> snapshot.
+bool texture_view(NcrTexture* tex, NcrCmd* view, DevRef* keep) {
+    memset(view, 0, sizeof(*view));
+    const void* p = nullptr;
+    uint32_t flags = 0;
+    if (!bind_texture(tex, &p, &flags, keep)) return false;
+    i64 w, h;
+    tex_dims(tex, &w, &h);
+    view->tex = p;
+    view->flags = flags;
+    view->tex_w = (int32_t)w;
+    view->tex_h = (int32_t)h;
+    return true;
+}
+
+}   // namespace
+
+// ------------------------------------------------------------------------------------------------
+// context lifecycle & readback
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+long GetBufferSize(RenderContext* ctx) {
+    NcrContext* c = live(ctx);
+    return c ? c->w * c->h * ipp_of(c) : 0;
+}
+
+RenderContext* CreateRenderContext(long width, long height, bool enableAlpha) {
+    if (!use_device()) return nullptr;
+    NcrContext* c = new NcrContext();
+    memset(&c->stats, 0, sizeof(c->stats));
+    memset(&c->last, 0, sizeof(c->last));
+    c->alpha = enableAlpha;
+    ncr_state_reset(c->st);
+    bool ok = CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int k = 0; ok && k < 4; ++k) ok = CK(cudaEventCreate(&c->ev[k]));
+    ok = ok && CK(cudaEventCreate(&c->ev_t0)) && CK(cudaEventCreate(&c->ev_t1));
+    for (int k = 0; ok && k < 2; ++k) ok = CK(cudaEventCreateWithFlags(&c->stg[k].done, cudaEventDisableTiming));
+    ok = ok && CK(cudaMallocHost((void**)&c->h_cursors, 8 * sizeof(uint32_t)));
+    ok = ok && alloc_canvas(c, width, height);
+    if (!ok) {
+        c->dead = true;
+        return nullptr;
+    }
+    return c;
+}
+
+void DestroyRenderContext(RenderContext* ctx) {
+    NcrContext* c = live(ctx);
+    if (!c || !use_device()) return;
+    cudaStreamSynchronize(c->stream);
+    c->dead = true;
+    c->fb.reset();
+    c->refs.clear();
+    c->last_refs.clear();
+    c->d_cmds.release(); c->d_boxes.release(); c->d_aux.release();
+    c->d_coarse.release(); c->d_coarse_off.release(); c->d_fine.release(); c->d_fine_off.release();
+    c->d_cursors.release(); c->d_u8.release();
+    for (int k = 0; k < 2; ++k) {
+        c->stg[k].cmds.release(); c->stg[k].boxes.release(); c->stg[k].aux.release();
+        if (c->stg[k].done) cudaEventDestroy(c->stg[k].done);
+    }
+    for (int k = 0; k < 4; ++k) cudaEventDestroy(c->ev[k]);
+    cudaEventDestroy(c->ev_t0);
+    cudaEventDestroy(c->ev_t1);
+    cudaFreeHost(c->h_cursors);
+    cudaStreamDestroy(c->stream);
+    // The small host object itself stays allocated (and marked dead) so that a stale handle is detected
+    // instead of dereferencing freed memory; the reference never frees anything at all (cpp:33-37).
+}
+
+void ResizeRenderContext(RenderContext* ctx, long width, long height) {
+    NcrContext* c = live(ctx);
+    if (!c || !use_device()) return;
+    // cpp:39-45: pixels are discarded, state is kept — pending draws can no longer be observed.
+    cudaStreamSynchronize(c->stream);
+    c->n = 0; c->n_aux = 0; c->coarse_need = c->fine_need = 0; c->load_fb = true;
+    c->refs.clear();
+    alloc_canvas(c, width, height);
+}
+
+void GetBuffer(RenderContext* ctx, double* buffer) {
+    NcrContext* c = live(ctx);
+    if (!c || !buffer) return;
+    if (!flush(c, false)) return;
+    const size_t bytes = (size_t)c->w * c->h * ipp_of(c) * sizeof(double);
+    if (bytes && !CK(cudaMemcpyAsync(buffer, c->fb->p, bytes, cudaMemcpyDeviceToHost, c->stream))) c->failed = true;
+    c->stats.d2h_bytes += bytes;
+    sync_ctx(c);
+}
+
+void GetBufferAsUInt8(RenderContext* ctx, unsigned char* buffer) {
+    NcrContext* c = live(ctx);
+    if (!c || !buffer) return;
+    if (!flush(c, true)) return;
+    const size_t bytes = (size_t)c->w * c->h * ipp_of(c);
+    if (bytes && !CK(cudaMemcpyAsync(buffer, c->d_u8.p, bytes, cudaMemcpyDeviceToHost, c->stream))) c->failed = true;
+    c->stats.d2h_bytes += bytes;
+    sync_ctx(c);
+}
+
+void GetColor(RenderContext* ctx, double x, double y, double* out_r, double* out_g, double* out_b, double* out_a) {
+    NcrContext* c = live(ctx);
+    if (!c || c->w <= 0 || c->h <= 0) return;
+    // cpp:664-670: clamp then truncate
+    if (x < 0) x = 0;
+    if (x >= c->w) x = c->w - 1;
+    if (y < 0) y = 0;
+    if (y >= c->h) y = c->h - 1;
+    i64 ix = ncr_trunc_i64(x), iy = ncr_trunc_i64(y);
+    ix = std::max((i64)0, std::min(c->w - 1, ix));
+    iy = std::max((i64)0, std::min(c->h - 1, iy));
+    if (!flush(c, false)) return;
+    double px[4] = {0, 0, 0, 0};
+    const int ipp = ipp_of(c);
+    if (!CK(cudaMemcpyAsync(px, (double*)c->fb->p + (iy * c->w + ix) * ipp, ipp * sizeof(double), cudaMemcpyDeviceToHost,
+                            c->stream)))
+        return;
+    if (!sync_ctx(c)) return;
+    if (out_r) *out_r = px[0];
+    if (out_g) *out_g = px[1];
+    if (out_b) *out_b = px[2];
+    if (c->alpha && out_a) *out_a = px[3];
+}
+
+// ------------------------------------------------------------------------------------------------
+// state machine (host only)
+// ------------------------------------------------------------------------------------------------
+void SaveContextState(RenderContext* ctx) {
+    NcrContext* c = live(ctx);
+    if (c) c->stack.push_back(c->st);
+}
+
+bool RestoreContextState(RenderContext* ctx) {
+    NcrContext* c = live(ctx);
+    if (!c || c->stack.empty()) return false;
+    c->st = c->stack.back();
+    c->stack.pop_back();
+    return true;
+}
+
+void SetTransform(RenderContext* ctx, double a, double b, double c_, double d, double e, double f) {
+    NcrContext* c = live(ctx);
+    if (!c) return;
+    c->st.m[0] = a; c->st.m[1] = b; c->st.m[2] = c_; c->st.m[3] = d; c->st.m[4] = e; c->st.m[5] = f;
+}
+
+void ApplyTransform(RenderContext* ctx, double a, double b, double c_, double d, double e, double f) {
+    NcrContext* c = live(ctx);
+    if (c) ncr_apply_transform(c->st.m, a, b, c_, d, e, f);
+}
+
+void Scale(RenderContext* ctx, double sx, double sy) {
+    NcrContext* c = live(ctx);
+    if (c) ncr_apply_transform(c->st.m, sx, 0, 0, sy, 0, 0);
+}
+
+void Translate(RenderContext* ctx, double tx, double ty) {
+    NcrContext* c = live(ctx);
+    if (c) ncr_apply_transform(c->st.m, 1, 0, 0, 1, tx, ty);
+}
+
+void Rotate(RenderContext* ctx, double angle) {
+    NcrContext* c = live(ctx);
+    if (!c) return;
+    const double s = sin(angle), co = cos(angle);   // host libm, as the reference (cpp:440-441)
+    ncr_apply_transform(c->st.m, co, s, -s, co, 0, 0);
+}
+
+void TransformPoint(RenderContext* ctx, double x, double y, double* out_x, double* out_y) {
+    NcrContext* c = live(ctx);
+    if (c && out_x && out_y) ncr_xform_point(c->st.m, x, y, out_x, out_y);
+}
+
+void GetTransform(RenderContext* ctx, double out_matrix[6]) {
+    NcrContext* c = live(ctx);
+    if (c) memcpy(out_matrix, c->st.m, sizeof(c->st.m));
+}
+
+void GetInverseTransform(RenderContext* ctx, double out_matrix[6]) {
+    NcrContext* c = live(ctx);
+    if (c) ncr_inverse(c->st.m, out_matrix);
+}
+
+void SetColorTransform(RenderContext* ctx, double r, double g, double b, double a) {
+    NcrContext* c = live(ctx);
+    if (!c) return;
+    c->st.ct[0] = r; c->st.ct[1] = g; c->st.ct[2] = b; c->st.ct[3] = a;
+}
+
+void ApplyColorTransform(RenderContext* ctx, double r, double g, double b, double a) {
+    NcrContext* c = live(ctx);
+    if (!c) return;
+    c->st.ct[0] *= r; c->st.ct[1] *= g; c->st.ct[2] *= b; c->st.ct[3] *= a;
+}
+
+// ------------------------------------------------------------------------------------------------
+// recorded pixel writes
+// ------------------------------------------------------------------------------------------------
+bool SetPixel(RenderContext* ctx, long x, long y, double r, double g, double b, double a) {
+    NcrContext* c = live(ctx);
+    if (!c) return false;
+    if (x < 0 || x >= c->w || y < 0 || y >= c->h) return false;   // cpp:499-502
+    NcrCmd* cmd = begin_cmd(c, NCR_OP_SET_PIXEL, x, x + 1, y, y + 1, false);
+    if (!cmd) return true;
+    cmd->p[0] = r; cmd->p[1] = g; cmd->p[2] = b; cmd->p[3] = a;
+    if (!c->alpha) {
+        // cpp:510 stores `a` at index+3 even on a 3-channel canvas: that element is the red of the next pixel
+        // in row-major order (past-the-end for the last pixel: out of bounds in the reference, dropped here).
+        i64 nx = x + 1, ny = y;
+        if (nx >= c->w) { nx = 0; ny = y + 1; }
+        if (ny < c->h) {
+            NcrCmd* spill = begin_cmd(c, NCR_OP_SET_PIXEL, nx, nx + 1, ny, ny + 1, false);
+            if (spill) { spill->p[0] = a; spill->p[4] = 1.0; }
+        }
+    }
+    return true;
+}
+
+bool ApplyPixel(RenderContext* ctx, long x, long y, double r, double g, double b, double a) {
+    NcrContext* c = live(ctx);
+    if (!c) return false;
+    if (x < 0 || x >= c->w || y < 0 || y >= c->h) return false;   // cpp:520-523
+    NcrCmd* cmd = begin_cmd(c, NCR_OP_APPLY_PIXEL, x, x + 1, y, y + 1, false);
+    if (cmd) { cmd->p[0] = r; cmd->p[1] = g; cmd->p[2] = b; cmd->p[3] = a; }
+    return true;
+}
+
+void SetColor(RenderContext* ctx, double r, double g, double b, double a) {
+    NcrContext* c = live(ctx);
+    if (!c || c->w <= 0 || c->h <= 0) return;
+    // Every pixel is overwritten (cpp:643-657), so nothing recorded before this call can be observed any more
+    // and the composite need not read the canvas back.
+    c->n = 0; c->n_aux = 0; c->coarse_need = c->fine_need = 0;
+    c->refs.clear();
+    NcrCmd* cmd = begin_cmd(c, NCR_OP_SET_COLOR, 0, c->w, 0, c->h, false);
+    if (!cmd) return;
+    c->load_fb = false;
+    const bool uniform = (r == g && g == b && b == a);   // cpp:647: std::fill of every element with r
+    cmd->p[0] = r; cmd->p[1] = g; cmd->p[2] = b; cmd->p[3] = a;
+    if (!c->alpha && !uniform) cmd->flags |= NCR_F_RGB_SPILL;   // SetPixel's index+3 store, see the kernel
+}
+
+void FillColor(RenderContext* ctx, double r, double g, double b, double a) {
+    NcrContext* c = live(ctx);
+    if (!c) return;
+    NcrCmd* cmd = begin_cmd(c, NCR_OP_FILL_COLOR, 0, c->w, 0, c->h);
+    if (cmd) { cmd->p[0] = r; cmd->p[1] = g; cmd->p[2] = b; cmd->p[3] = a; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// recorded primitives
+// ------------------------------------------------------------------------------------------------
+static void fill_texture_fields(NcrContext* c, NcrCmd* cmd, const void* ptr, uint32_t tflags, const DevRef& keep, i64 tw, i64 th) {
+    cmd->tex = ptr;
+    cmd->flags |= tflags;
+    if (c->sampling == 1) cmd->flags |= NCR_F_BILINEAR;
+    cmd->tex_w = (int32_t)tw;
+    cmd->tex_h = (int32_t)th;
+    keep_ref(c, keep);
+}
+
+void DrawTexture(RenderContext* ctx, Texture* tex_, double x, double y, double width, double height) {
+    NcrContext* c = live(ctx);
+    NcrTexture* tex = live(tex_);
+    if (!c || !tex) return;
+    if (width == 0 || height == 0) return;   // cpp:726
+    i64 tw, th;
+    tex_dims(tex, &tw, &th);
+    const double scaleX = tw / width, scaleY = th / height;   // cpp:728-729
+    const void* ptr; uint32_t tflags; DevRef keep;
+    if (ncr_is_no_transform(c->st.m)) {
+        // cpp:741-742: for (i64 i = x; i < x + width; ++i) — the matrix is ignored, ApplyPixel clips.
+        const i64 i0 = ncr_trunc_i64(x), j0 = ncr_trunc_i64(y);
+        const double xw = x + width, yh = y + height;
+        const double cr = ceil(xw), cb = ceil(yh);
+        const i64 l = std::max((i64)0, std::min(c->w, i0)), t = std::max((i64)0, std::min(c->h, j0));
+        const i64 r = !(cr > 0) ? 0 : (cr >= (double)c->w ? c->w : (i64)cr);
+        const i64 b = !(cb > 0) ? 0 : (cb >= (double)c->h ? c->h : (i64)cb);
+        if (l >= r || t >= b) return;
+        if (!bind_texture(tex, &ptr, &tflags, &keep)) return;
+        NcrCmd* cmd = begin_cmd(c, NCR_OP_TEX_IDENT, l, r, t, b);
+        if (!cmd) return;
+        fill_texture_fields(c, cmd, ptr, tflags, keep, tw, th);
+        cmd->x = x; cmd->y = y; cmd->xw = xw; cmd->yh = yh;
+        cmd->sx = scaleX; cmd->sy = scaleY;
+        cmd->p[0] = (double)i0; cmd->p[1] = (double)j0;
+        return;
+    }
+    i64 l, r, t, b;
+    ncr_border(c->st.m, x, y, width, height, c->w, c->h, &l, &r, &t, &b);
+    if (l >= r || t >= b) return;
+    if (!bind_texture(tex, &ptr, &tflags, &keep)) return;
+    NcrCmd* cmd = begin_cmd(c, NCR_OP_TEX, l, r, t, b);
+    if (!cmd) return;
+    fill_texture_fields(c, cmd, ptr, tflags, keep, tw, th);
+    put_inverse(c, cmd);
+    cmd->x = x; cmd->y = y; cmd->xw = x + width; cmd->yh = y + height;
+    cmd->sx = scaleX; cmd->sy = scaleY;
+}
+
+void DrawSplittedTexture(RenderContext* ctx, Texture* tex_, double x, double y, double width, double height, double uStart,
+                         double uEnd, double vStart, double vEnd) {
+    NcrContext* c = live(ctx);
+    NcrTexture* tex = live(tex_);
+    if (!c || !tex) return;
+    if (width == 0 || height == 0) return;   // cpp:789
+    i64 tw, th;
+    tex_dims(tex, &tw, &th);
+    i64 l, r, t, b;
+    ncr_border(c->st.m, x, y, width, height, c->w, c->h, &l, &r, &t, &b);
+    if (l >= r || t >= b) return;
+    const void* ptr; uint32_t tflags; DevRef keep;
+    if (!bind_texture(tex, &ptr, &tflags, &keep)) return;
+    NcrCmd* cmd = begin_cmd(c, NCR_OP_TEX_SPLIT, l, r, t, b);
+    if (!cmd) return;
+    fill_texture_fields(c, cmd, ptr, tflags, keep, tw, th);
+    put_inverse(c, cmd);
+    cmd->x = x; cmd->y = y; cmd->xw = x + width; cmd->yh = y + height;
+    cmd->sx = tw / width; cmd->sy = th / height;   // cpp:793-794
+    // cpp:812-813: u = (uStart + (uEnd - uStart) * u / tex->width) * tex->width
+    cmd->p[0] = uStart; cmd->p[1] = uEnd - uStart;
+    cmd->p[2] = vStart; cmd->p[3] = vEnd - vStart;
+    cmd->p[4] = (double)tw; cmd->p[5] = (double)th;
+}
+
+void DrawRect(RenderContext* ctx, double x, double y, double width, double height, double r_, double g, double b_, double a) {
+    NcrContext* c = live(ctx);
+    if (!c) return;
+    if (width <= 0 || height <= 0) return;   // cpp:853
+    i64 l, r, t, b;
+    ncr_border(c->st.m, x, y, width, height, c->w, c->h, &l, &r, &t, &b);
+    NcrCmd* cmd = begin_cmd(c, NCR_OP_RECT, l, r, t, b);
+    if (!cmd) return;
+    put_inverse(c, cmd);
+    cmd->x = x; cmd->y = y; cmd->xw = x + width; cmd->yh = y + height;
+    cmd->p[0] = r_; cmd->p[1] = g; cmd->p[2] = b_; cmd->p[3] = a;
+}
+
+void DrawVerticalGrd(RenderContext* ctx, double x, double y, double width, double height, double top_r, double top_g,
+                     double top_b, double top_a, double bottom_r, double bottom_g, double bottom_b, double bottom_a) {
+    NcrContext* c = live(ctx);
+    if (!c) return;
+    if (width <= 0 || height <= 0) return;   // cpp:1291
+    i64 l, r, t, b;
+    ncr_border(c->st.m, x, y, width, height, c->w, c->h, &l, &r, &t, &b);
+    NcrCmd* cmd = begin_cmd(c, NCR_OP_GRAD, l, r, t, b);
+    if (!cmd) return;
+    put_inverse(c, cmd);
+    cmd->x = x; cmd->y = y; cmd->xw = x + width; cmd->yh = y + height;
+    cmd->sy = height;   // cpp:1308: p = (invY - y) / height
+    cmd->p[0] = top_r; cmd->p[1] = top_g; cmd->p[2] = top_b; cmd->p[3] = top_a;
+    cmd->p[4] = bottom_r - top_r; cmd->p[5] = bottom_g - top_g;   // cpp:1309-1312
+    cmd->p[6] = bottom_b - top_b; cmd->p[7] = bottom_a - top_a;
+}
+
+void DrawCircle(RenderContext* ctx, double x, double y, double radius, double r_, double g, double b_, double a) {
+    NcrContext* c = live(ctx);
+    if (!c) return;
+    if (radius <= 0) return;   // cpp:926
+    i64 l, r, t, b;
+    ncr_border(c->st.m, x - radius, y - radius, 2 * radius, 2 * radius, c->w, c->h, &l, &r, &t, &b);   // cpp:932
+    NcrCmd* cmd = begin_cmd(c, NCR_OP_CIRCLE, l, r, t, b);
+    if (!cmd) return;
+    put_inverse(c, cmd);
+    cmd->x = x; cmd->y = y; cmd->sx = radius;
+    cmd->p[0] = r_; cmd->p[1] = g; cmd->p[2] = b_; cmd->p[3] = a;
+}
+
+// Polygon fill in inverse-mapped space (cpp:908-916).  The reference scans the whole canvas; the recorded box is
+// a conservative cover of the forward-mapped polygon (full canvas whenever the cover cannot be trusted).
+static void record_polygon(NcrContext* c, const double* pts, size_t n, double r_, double g, double b_, double a) {
+    if (n == 0) return;
+    const double* m = c->st.m;
+    i64 l = 0, r = c->w, t = 0, b = c->h;
+    const double det = m[0] * m[3] - m[1] * m[2];
+    const double norm2 = m[0] * m[0] + m[1] * m[1] + m[2] * m[2] + m[3] * m[3];
+    bool tight = det != 0 && isfinite(det) && isfinite(norm2) && isfinite(m[4]) && isfinite(m[5]);
+    if (tight) {
+        double minx = INFINITY, maxx = -INFINITY, miny = INFINITY, maxy = -INFINITY, mag = fabs(m[4]) + fabs(m[5]);
+        for (size_t k = 0; k < n; ++k) {
+            double fx, fy;
+            ncr_xform_point(m, pts[2 * k], pts[2 * k + 1], &fx, &fy);
+            if (!isfinite(fx) || !isfinite(fy)) { tight = false; break; }
+            minx = std::min(minx, fx); maxx = std::max(maxx, fx);
+            miny = std::min(miny, fy); maxy = std::max(maxy, fy);
+            mag = std::max(mag, fabs(pts[2 * k]) * sqrt(norm2) + fabs(pts[2 * k + 1]) * sqrt(norm2));
+        }
+        // Rounding in inv / the per-pixel inverse map moves the boundary by about cond(M) * |coords| * 2^-52 px.
+        const double cond = norm2 / fabs(det);
+        const double slack = cond * (mag + (double)c->w + (double)c->h) * 1e-14;
+        if (tight && slack < 0.25) {
+            const double pad = 2.0;
+            const double L = floor(minx - pad), R = ceil(maxx + pad) + 1, T = floor(miny - pad), B = ceil(maxy + pad) + 1;
+            l = L <= 0 ? 0 : (L >= (double)c->w ? c->w : (i64)L);
+            r = R <= 0 ? 0 : (R >= (double)c->w ? c->w : (i64)R);
+            t = T <= 0 ? 0 : (T >= (double)c->h ? c->h : (i64)T);
+            b = B <= 0 ? 0 : (B >= (double)c->h ? c->h : (i64)B);
+        }
+    }
+    NcrCmd* cmd = begin_cmd(c, NCR_OP_POLY, l, r, t, b, true, 2 * n);
+    if (!cmd) return;
+    put_inverse(c, cmd);
+    NcrStaging& S = c->stg[c->cur];
+    cmd->aux_off = (uint32_t)c->n_aux;
+    cmd->aux_n = (uint32_t)n;
+    memcpy(S.aux.p + c->n_aux, pts, 2 * n * sizeof(double));
+    c->n_aux += 2 * n;
+    cmd->p[0] = r_; cmd->p[1] = g; cmd->p[2] = b_; cmd->p[3] = a;
+}
+
+void DrawLine(RenderContext* ctx, double x1, double y1, double x2, double y2, double width, double r, double g, double b,
+              double a) {
+    NcrContext* c = live(ctx);
+    if (!c) return;
+    if (width <= 0) return;   // cpp:883
+    // cpp:888-906: the stroke is the 4-gon endpoints -/+ unit normal * width/2
+    const double dx = x2 - x1, dy = y2 - y1;
+    const double len = sqrt(dx * dx + dy * dy);
+    if (len == 0) return;
+    const double ux = dx / len, uy = dy / len;
+    const double vx = -uy, vy = ux;
+    const double hw = width / 2;
+    const double pts[8] = {x1 - vx * hw, y1 - vy * hw, x1 + vx * hw, y1 + vy * hw,
+                           x2 + vx * hw, y2 + vy * hw, x2 - vx * hw, y2 - vy * hw};
+    record_polygon(c, pts, 4, r, g, b, a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// textures
+// ------------------------------------------------------------------------------------------------
+Texture* CreateTexture(long width, long height, bool enableAlpha, double* buffer) {
+    return new_texture(width, height, enableAlpha, true, buffer);
+}
+
+Texture* CreateTextureUInt8(long width, long height, bool enableAlpha, unsigned char* buffer) {
+    // cpp:350 stores u8 / 255.0; the bytes stay bytes in HBM and are decoded with the same division in-kernel.
+    return new_texture(width, height, enableAlpha, false, buffer);
+}
+
+void DestroyTexture(Texture* tex_) {
+    NcrTexture* tex = live(tex_);
+    if (!tex) return;
+    // Recorded commands hold their own reference to the texels, so dropping ours is safe at any time.
+    tex->dead = true;
+    tex->buf.reset();
+    tex->shadow.clear();
+    tex->shadow.shrink_to_fit();
+}
+
+Texture* CreateTextureFromRenderContext(RenderContext* ctx) {
+    NcrContext* c = live(ctx);
+    if (!c) return nullptr;
+    if (!flush(c, false)) return nullptr;
+    NcrTexture* t = new_texture(c->w, c->h, c->alpha, true, nullptr);
+    if (!t) return nullptr;
+    const size_t bytes = (size_t)c->w * c->h * ipp_of(c) * sizeof(double);
+    if (bytes && !CK(cudaMemcpyAsync(t->buf->p, c->fb->p, bytes, cudaMemcpyDeviceToDevice, c->stream))) return nullptr;
+    sync_ctx(c);
+    return t;
+}
+
+Texture* CreateTextureFromRenderContextShared(RenderContext* ctx) {
+    NcrContext* c = live(ctx);
+    if (!c) return nullptr;
+    NcrTexture* t = new NcrTexture();
+    t->w = c->w; t->h = c->h; t->alpha = c->alpha; t->is_f64 = true;
+    t->alias = c;
+    return t;
+}
+
+long GetTextureWidth(Texture* tex_) {
+    NcrTexture* tex = live(tex_);
+    if (!tex) return 0;
+    i64 w, h;
+    tex_dims(tex, &w, &h);
+    return w;
+}
+
+long GetTextureHeight(Texture* tex_) {
+    NcrTexture* tex = live(tex_);
+    if (!tex) return 0;
+    i64 w, h;
+    tex_dims(tex, &w, &h);
+    return h;
+}
+
+bool GetTextureEnableAlpha(Texture* tex_) {
+    NcrTexture* tex = live(tex_);
+    return tex ? tex->alpha : false;
+}
+
+Texture* ResampleTexture(Texture* tex_, long width, long height) {
+    NcrTexture* tex = live(tex_);
+    if (!tex || !use_device()) return nullptr;
+    NcrCmd view;
+    DevRef keep;
+    if (!texture_view(tex, &view, &keep)) return nullptr;
+    const bool f64 = (view.flags & NCR_F_TEX_F64) != 0, alpha = (view.flags & NCR_F_TEX_ALPHA) != 0;
+    NcrTexture* out = new_texture(width, height, alpha, f64, nullptr);
+    if (!out) return nullptr;
+    if (width > 0 && height > 0) {
+        ncr_launch_resample(&view, out->buf->p, (int)width, (int)height, 0);
+        g_launches += 1;
+        if (!CK(cudaGetLastError()) || !CK(cudaStreamSynchronize(0))) return nullptr;
+    }
+    return out;
+}
+
+void GetMilthmHitEffectPixel(double seed, double t, double x, double y, double* a) {
+    if (a) *a = ncr_hit_effect_alpha(seed, t, x, y);
+}
+
+Texture* CreateMilthmHitEffectTexture(Texture* mask_, double seed, double t, double r, double g, double b) {
+    NcrTexture* mask = live(mask_);
+    if (!mask || !use_device()) return nullptr;
+    if (!mask->alpha) return nullptr;   // cpp:1418
+    const i64 w = mask->w, h = mask->h;
+    const size_t n = (size_t)w * h;
+    // The noise uses libm sin/atan2 (cpp:1339-1389) and is thresholded, so it is evaluated on the host to stay
+    // bit-identical; only the mask's alpha plane is needed from the device (fetched once per mask).
+    std::vector<double> mask_a(n);
+    if (mask->alias || mask->is_f64) {
+        NcrCmd view; DevRef keep;
+        if (!texture_view(mask, &view, &keep)) return nullptr;
+        std::vector<double> all(n * 4);
+        if (n && !CK(cudaMemcpy(all.data(), view.tex, n * 4 * sizeof(double), cudaMemcpyDeviceToHost))) return nullptr;
+        for (size_t k = 0; k < n; ++k) mask_a[k] = all[4 * k + 3];
+    } else {
+        if (mask->shadow.size() != n * 4) {
+            mask->shadow.resize(n * 4);
+            if (n && !CK(cudaMemcpy(mask->shadow.data(), mask->buf->p, n * 4, cudaMemcpyDeviceToHost))) return nullptr;
+        }
+        for (size_t k = 0; k < n; ++k) mask_a[k] = mask->shadow[4 * k + 3] / 255.0;
+    }
+    // cpp:1426-1436 indexes mask and output as [i*height*4 + j*4] (i over width): linear element i*h + j.
+    std::vector<double> out(n * 4);
+    bool bytes_exact = true;
+    for (i64 i = 0; i < w; ++i) {
+        for (i64 j = 0; j < h; ++j) {
+            const double av = ncr_hit_effect_alpha(seed, t, (double)i / w, (double)j / h);
+            const size_t k = (size_t)i * h + j;
+            out[4 * k + 0] = r; out[4 * k + 1] = g; out[4 * k + 2] = b;
+            out[4 * k + 3] = av * mask_a[k];
+        }
+    }
+    // Store as RGBA8 when every element is exactly some k/255.0 (true for milrenderer's call, pyb:45-47).
+    unsigned char rgb8[3];
+    const double rgbv[3] = {r, g, b};
+    for (int ch = 0; ch < 3 && bytes_exact; ++ch) {
+        const double s = rgbv[ch] * 255.0;
+        const long k = lrint(s);
+        if (k < 0 || k > 255 || (double)k / 255.0 != rgbv[ch]) bytes_exact = false;
+        else rgb8[ch] = (unsigned char)k;
+    }
+    std::vector<unsigned char> out8;
+    if (bytes_exact) {
+        out8.resize(n * 4);
+        for (size_t k = 0; k < n && bytes_exact; ++k) {
+            const double av = out[4 * k + 3];
+            const long q = lrint(av * 255.0);
+            if (q < 0 || q > 255 || (double)q / 255.0 != av) { bytes_exact = false; break; }
+            out8[4 * k + 0] = rgb8[0]; out8[4 * k + 1] = rgb8[1]; out8[4 * k + 2] = rgb8[2];
+            out8[4 * k + 3] = (unsigned char)q;
+        }
+    }
+    if (bytes_exact) return new_texture(w, h, true, false, out8.data());
+    return new_texture(w, h, true, true, out.data());
+}
+
+long GetVersion(void) { return 1; }   // h:9
+
+// ------------------------------------------------------------------------------------------------
+// additive entry points
+// ------------------------------------------------------------------------------------------------
+int NcrFlush(RenderContext* ctx) {
+    NcrContext* c = live(ctx);
+    if (!c) return -1;
+    if (!flush(c, false)) return -1;
+    return sync_ctx(c) ? 0 : -1;
+}
+
+const char* NcrLastError(void) { return g_err; }
+const char* NcrDeviceName(void) { return g_devname; }
+
+void* NcrAllocHost(unsigned long long bytes) {
+    if (!use_device()) return nullptr;
+    void* p = nullptr;
+    if (!CK(cudaMallocHost(&p, bytes ? bytes : 16))) return nullptr;
+    return p;
+}
+
+void NcrFreeHost(void* p) {
+    if (p && use_device()) cudaFreeHost(p);
+}
+
+void NcrGetStats(RenderContext* ctx, NcrStats* out) {
+    NcrContext* c = live(ctx);
+    if (!c || !out) return;
+    if (use_device()) sync_ctx(c);
+    *out = c->stats;
+}
+
+void NcrSetStatsMode(RenderContext* ctx, int mode) {
+    NcrContext* c = live(ctx);
+    if (c) c->stats_mode = mode;
+}
+
+unsigned long long NcrKernelLaunchCount(void) { return g_launches.load(); }
+
+int NcrRerunLastFlush(RenderContext* ctx, int iters, int flush_l2, float* ms_out) {
+    NcrContext* c = live(ctx);
+    if (!c || !c->has_last || !use_device()) return -1;
+    if (!sync_ctx(c)) return -1;
+    if (flush_l2 && !g_l2_scrub) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!g_l2_scrub && cudaMalloc(&g_l2_scrub, kL2ScrubBytes) != cudaSuccess) return -1;
+    }
+    for (int it = 0; it < iters; ++it) {
+        if (flush_l2) cudaMemsetAsync(g_l2_scrub, it & 0xff, kL2ScrubBytes, c->stream);
+        cudaEventRecord(c->ev_t0, c->stream);
+        ncr_launch_flush(&c->last, c->stream, nullptr);
+        cudaEventRecord(c->ev_t1, c->stream);
+        g_launches += 3;
+        c->stats.kernel_launches += 3;
+        if (!CK(cudaStreamSynchronize(c->stream))) { c->failed = true; return -1; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1);
+        if (ms_out) ms_out[it] = ms;
+    }
+    c->u8_valid = c->last.u8_out != nullptr;
+    return 0;
+}
+
+void NcrSetClipRect(RenderContext* ctx, long x, long y, long width, long height) {
+    NcrContext* c = live(ctx);
+    if (!c) return;
+    c->clip_on = true;
+    c->clip_l = std::max((i64)0, (i64)x);
+    c->clip_t = std::max((i64)0, (i64)y);
+    c->clip_r = std::min(c->w, (i64)(x + width));
+    c->clip_b = std::min(c->h, (i64)(y + height));
+}
+
+void NcrClearClipRect(RenderContext* ctx) {
+    NcrContext* c = live(ctx);
+    if (c) c->clip_on = false;
+}
+
+void NcrSetSampling(RenderContext* ctx, int mode) {
+    NcrContext* c = live(ctx);
+    if (c) c->sampling = mode == 1 ? 1 : 0;
+}
+
+void NcrFillPolygon(RenderContext* ctx, const double* xy, long n_points, double r, double g, double b, double a) {
+    NcrContext* c = live(ctx);
+    if (!c || !xy || n_points <= 0) return;
+    record_polygon(c, xy, (size_t)n_points, r, g, b, a);
+}
+
+void NcrDrawTexturePerspective(RenderContext* ctx, Texture* tex_, const double inv_h[9], double x, double y, double width,
+                               double height) {
+    NcrContext* c = live(ctx);
+    NcrTexture* tex = live(tex_);
+    if (!c || !tex || !inv_h) return;
+    if (width == 0 || height == 0) return;
+    i64 tw, th;
+    tex_dims(tex, &tw, &th);
+    const void* ptr; uint32_t tflags; DevRef keep;
+    if (!bind_texture(tex, &ptr, &tflags, &keep)) return;
+    // No forward map is available for a general projective inverse: cover the canvas (or the clip rect).
+    NcrCmd* cmd = begin_cmd(c, NCR_OP_TEX_PERSP, 0, c->w, 0, c->h);
+    if (!cmd) return;
+    fill_texture_fields(c, cmd, ptr, tflags, keep, tw, th);
+    for (int k = 0; k < 6; ++k) cmd->inv[k] = inv_h[k];
+    cmd->p[0] = inv_h[6]; cmd->p[1] = inv_h[7]; cmd->p[2] = inv_h[8];
+    cmd->x = x; cmd->y = y; cmd->xw = x + width; cmd->yh = y + height;
+    cmd->sx = tw / width; cmd->sy = th / height;
+}
+
+long NcrSubmitTrace(RenderContext* ctx, const void* trace, long bytes, Texture* const* textures, long n_textures) {
+    NcrContext* c = live(ctx);
+    if (!c || !trace || bytes < 0) return -1;
+    const unsigned char* p = (const unsigned char*)trace;
+    const unsigned char* end = p + bytes;
+    long executed = 0;
+    while (p + sizeof(NcrTraceRec) <= end) {
+        NcrTraceRec rec;
+        memcpy(&rec, p, sizeof(rec));
+        p += sizeof(rec);
+        if ((size_t)(end - p) < (size_t)rec.n * sizeof(double)) return -1;
+        const double* a = (const double*)p;   // records are 8-byte aligned by construction
+        p += (size_t)rec.n * sizeof(double);
+        Texture* tex = nullptr;
+        if (rec.op == NCR_T_DRAW_TEXTURE || rec.op == NCR_T_DRAW_SPLIT || rec.op == NCR_T_DRAW_PERSP) {
+            if (rec.n < 1) return -1;
+            const long slot = (long)a[0];
+            if (slot < 0 || slot >= n_textures) return -1;
+            tex = textures[slot];
+        }
+#define NEED(k) if (rec.n != (k)) return -1
+        switch (rec.op) {
+            case NCR_T_SAVE: SaveContextState(ctx); break;
+            case NCR_T_RESTORE: RestoreContextState(ctx); break;
+            case NCR_T_SET_TRANSFORM: NEED(6); SetTransform(ctx, a[0], a[1], a[2], a[3], a[4], a[5]); break;
+            case NCR_T_APPLY_TRANSFORM: NEED(6); ApplyTransform(ctx, a[0], a[1], a[2], a[3], a[4], a[5]); break;
+            case NCR_T_SCALE: NEED(2); Scale(ctx, a[0], a[1]); break;
+            case NCR_T_TRANSLATE: NEED(2); Translate(ctx, a[0], a[1]); break;
+            case NCR_T_ROTATE: NEED(1); Rotate(ctx, a[0]); break;
+            case NCR_T_SET_CT: NEED(4); SetColorTransform(ctx, a[0], a[1], a[2], a[3]); break;
+            case NCR_T_APPLY_CT: NEED(4); ApplyColorTransform(ctx, a[0], a[1], a[2], a[3]); break;
+            case NCR_T_SET_COLOR: NEED(4); SetColor(ctx, a[0], a[1], a[2], a[3]); break;
+            case NCR_T_FILL_COLOR: NEED(4); FillColor(ctx, a[0], a[1], a[2], a[3]); break;
+            case NCR_T_DRAW_TEXTURE: NEED(5); DrawTexture(ctx, tex, a[1], a[2], a[3], a[4]); break;
+            case NCR_T_DRAW_SPLIT: NEED(9); DrawSplittedTexture(ctx, tex, a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8]); break;
+            case NCR_T_DRAW_RECT: NEED(8); DrawRect(ctx, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]); break;
+            case NCR_T_DRAW_LINE: NEED(9); DrawLine(ctx, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8]); break;
+            case NCR_T_DRAW_CIRCLE: NEED(7); DrawCircle(ctx, a[0], a[1], a[2], a[3], a[4], a[5], a[6]); break;
+            case NCR_T_DRAW_GRD: NEED(12); DrawVerticalGrd(ctx, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11]); break;
+            case NCR_T_SET_PIXEL: NEED(6); SetPixel(ctx, (long)a[0], (long)a[1], a[2], a[3], a[4], a[5]); break;
+            case NCR_T_APPLY_PIXEL: NEED(6); ApplyPixel(ctx, (long)a[0], (long)a[1], a[2], a[3], a[4], a[5]); break;
+            case NCR_T_PRESENT: break;   // frame boundary: the caller reads back
+            case NCR_T_CLIP_SET: NEED(4); NcrSetClipRect(ctx, (long)a[0], (long)a[1], (long)a[2], (long)a[3]); break;
+            case NCR_T_CLIP_CLEAR: NcrClearClipRect(ctx); break;
+            case NCR_T_SAMPLING: NEED(1); NcrSetSampling(ctx, (int)a[0]); break;
+            case NCR_T_FILL_POLY:
+                if (rec.n < 6 || (rec.n & 1)) return -1;
+                NcrFillPolygon(ctx, a + 4, (rec.n - 4) / 2, a[0], a[1], a[2], a[3]);
+                break;
+            case NCR_T_DRAW_PERSP: NEED(14); NcrDrawTexturePerspective(ctx, tex, a + 1, a[10], a[11], a[12], a[13]); break;
+            default: return -1;
+        }
+#undef NEED
+        ++executed;
+    }
+    return executed;
+}
+
+}   // extern "C"

@@ -1,0 +1,18 @@
+// Launch interface between the host runtime (api.cu) and the kernels (kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include "ncr_cmd.h"
+
+// Alpha read from a 3-channel texture.  The reference leaves it uninitialised (cpp:746-748 with
+// cpp:571-573: `a` is only written when the texture has alpha), so its output there is garbage that
+// changes from call to call; the product defines it as opaque.  See DESIGN.md "Undefined in the reference".
+#define NCR_RGB_TEXTURE_ALPHA 1.0
+
+extern "C" {
+// memset cursors, bin (coarse, fine), composite — all on stream s.  ev: 4 events recorded around the
+// three kernels (timing mode) or nullptr.
+void ncr_launch_flush(const NcrFlushArgs* A, cudaStream_t s, cudaEvent_t* ev);
+void ncr_launch_convert_u8(const double* fb, unsigned char* out, size_t n, cudaStream_t s);
+void ncr_launch_resample(const NcrCmd* src, void* out, int ow, int oh, cudaStream_t s);
+}

@@ -1,0 +1,86 @@
+// Draw-command encoding shared by the host recorder and the sm_100a kernels.
+//
+// One NcrCmd is the snapshot the reference takes implicitly when a draw call runs
+// (reference src/libNativeCPURenderer.cpp:720-948, 1285-1316): the inverse matrix
+// (cpp:472-492), the GetBoarder pixel box (cpp:693-718), the colour transform
+// (cpp:525-528) and the call's own parameters.  Everything that is a pure function
+// of the call arguments is evaluated ONCE on the host with the reference's expression
+// trees; the kernels evaluate only the per-pixel part.
+#pragma once
+#include <stdint.h>
+
+enum NcrOp : uint32_t {
+    NCR_OP_NOP = 0,
+    NCR_OP_SET_COLOR = 1,    // cpp:643-657  store (p[0..3]) to every pixel
+    NCR_OP_FILL_COLOR = 2,   // cpp:682-691  APPLY (p[0..3]) on every pixel
+    NCR_OP_TEX_IDENT = 3,    // cpp:731-751  DrawTexture, "no transform" path
+    NCR_OP_TEX = 4,          // cpp:753-778  DrawTexture, inverse-mapped path
+    NCR_OP_TEX_SPLIT = 5,    // cpp:781-820  DrawSplittedTexture
+    NCR_OP_RECT = 6,         // cpp:847-874
+    NCR_OP_GRAD = 7,         // cpp:1285-1316 DrawVerticalGrd
+    NCR_OP_CIRCLE = 8,       // cpp:920-948
+    NCR_OP_POLY = 9,         // cpp:876-918 DrawLine's 4-gon / extension: N-gon fill
+    NCR_OP_SET_PIXEL = 10,   // cpp:494-513
+    NCR_OP_APPLY_PIXEL = 11, // cpp:515-549
+    NCR_OP_TEX_PERSP = 12,   // extension (parity unpinned): projective inverse map
+    NCR_OP_COUNT
+};
+
+// NcrCmd.flags
+enum : uint32_t {
+    NCR_F_TEX_ALPHA = 1u << 0,    // texture has 4 channels (else 3; alpha then reads as 1.0)
+    NCR_F_TEX_F64 = 1u << 1,      // texels are f64 (else u8 decoded through the k/255.0 table)
+    NCR_F_BILINEAR = 1u << 2,     // extension (parity unpinned): cpp:575-620 formula
+    NCR_F_CLIP = 1u << 3,         // extension: box already intersected with the clip rect on the host
+    NCR_F_RGB_SPILL = 1u << 4,    // SetPixel/SetColor on a 3-channel canvas: alpha lands in the next element (cpp:510)
+};
+
+struct alignas(16) NcrCmd {
+    uint32_t op;
+    uint32_t flags;
+    int32_t l, r, t, b;       // pixel box [l,r) x [t,b): loop bounds of the reference (bbox ops) or a conservative cover
+    int32_t tex_w, tex_h;
+    const void* tex;          // device pointer to texels, row-major [y][x][ipp]
+    uint32_t aux_off;         // NCR_OP_POLY: first point in the aux f64 array (x0,y0,x1,y1,...)
+    uint32_t aux_n;           // NCR_OP_POLY: number of points
+    double inv[6];            // inverse transform (cpp:483-491)
+    double x, y, xw, yh;      // x, y, x+width, y+height (the four inclusive bounds, cpp:765-768)
+    double sx, sy;            // scaleX, scaleY (cpp:728-729); GRAD: sy = height; CIRCLE: sx = radius
+    double ct[4];             // colour transform snapshot
+    double p[8];              // op-specific, see the recorder
+};
+static_assert(sizeof(NcrCmd) == 240, "NcrCmd layout");
+#define NCR_CMD_WORDS16 (sizeof(NcrCmd) / 16)
+
+// Compact per-command box, read by the binning kernels (16 B, coalesced).
+struct alignas(16) NcrBox {
+    int32_t l, r, t, b;
+};
+
+#define NCR_TILE 16            // composite tile edge in pixels
+#define NCR_COARSE 8           // coarse bin edge in tiles (128 px)
+
+struct NcrFrameDims {
+    int32_t w, h, ipp;
+    int32_t tiles_x, tiles_y;
+    int32_t bins_x, bins_y;
+};
+
+// Launch-side description of one flush (one canvas, one ordered command batch).
+struct NcrFlushArgs {
+    NcrFrameDims d;
+    double* fb;                 // canonical f64 canvas [h][w][ipp]
+    unsigned char* u8_out;      // fused (iu8)(v*255) image, or nullptr
+    const NcrCmd* cmds;
+    const NcrBox* boxes;
+    const double* aux;
+    uint32_t n_cmds;
+    uint32_t load_fb;           // 0: every tile's list starts with SET_COLOR, do not read fb
+    uint32_t* coarse_list;      // capacity coarse_cap
+    uint32_t* coarse_off;       // [bins] offset, [bins] count
+    uint32_t* fine_list;        // capacity fine_cap
+    uint32_t* fine_off;         // [tiles] offset, [tiles] count
+    uint32_t* cursors;          // [0] coarse cursor, [1] fine cursor, [2..3] blended-pixel counter (u64)
+    uint32_t coarse_cap, fine_cap;
+    uint32_t count_pixels;      // stats mode: count APPLY executions
+};

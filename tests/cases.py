@@ -1,0 +1,188 @@
+"""Parity cases shared by the golden generator, the CPU tests and the GPU tests.
+
+Each case is ``fn(renderer, image_rgba) -> {"u8": sha1, "f64": sha1, ...}`` and runs the same calls on
+whichever library ``renderer`` wraps (reference build, C restatement, product)."""
+from __future__ import annotations
+
+import hashlib
+
+import numpy as np
+
+from libnativecpurenderer_b200 import streams
+
+
+def sha(b) -> str:
+    return hashlib.sha1(bytes(b)).hexdigest()
+
+
+def digest(ctx) -> dict:
+    return {"u8": sha(ctx.get_buffer_as_uint8()), "f64": sha(ctx.get_buffer_np().tobytes())}
+
+
+def tiny_textures(R, image_rgba):
+    rs = np.random.RandomState(99)
+    return [
+        R.Texture.from_numpy(image_rgba),
+        R.Texture.from_numpy(rs.randint(0, 256, (9, 5, 4)).astype(np.uint8)),
+        R.Texture.from_numpy(rs.randint(0, 256, (2, 2, 4)).astype(np.uint8)),
+        R.Texture.from_numpy(rs.randint(0, 256, (33, 64, 4)).astype(np.uint8)),
+    ]
+
+
+# ---- SURVEY.md §8c known answers -----------------------------------------------------------------
+def case_k1(R, image_rgba):
+    ctx = R.RenderContext(1920, 1080, True)
+    streams.stream_k1(ctx, R.Texture.from_numpy(image_rgba))
+    return digest(ctx)
+
+
+def case_k2(R, image_rgba):
+    ctx = R.RenderContext(256, 256, True)
+    ctx.scale(.25, .25)
+    t16 = R.Texture.from_numpy(image_rgba).resample(16, 16)
+    out = {}
+    for i in range(121):
+        streams.stream_k2_frame(ctx, t16, i)
+        if i in (0, 1, 30, 60, 120):
+            out[f"u8_{i}"] = sha(ctx.get_buffer_as_uint8())
+    return out
+
+
+def case_k3(R, image_rgba):
+    """resample(16,16) of image.png, drawn 1:1 so the texels are observable through the ABI."""
+    t16 = R.Texture.from_numpy(image_rgba).resample(16, 16)
+    ctx = R.RenderContext(20, 20, True)
+    ctx.set_color(0, 0, 0, 0)
+    ctx.draw_texture(t16, 0, 0, 16, 16)
+    d = digest(ctx)
+    d["size"] = [t16.width, t16.height, int(t16.enableAlpha)]
+    return d
+
+
+def case_k4(R, image_rgba):
+    """CreateMilthmHitEffectTexture on image.png.resample(64,48) (non-square: exercises the transposed indexing)."""
+    mask = R.Texture.from_numpy(image_rgba).resample(64, 48)
+    fx = R.Helpers.create_milthm_hit_effect_textures(mask, 3, seed=0.25)
+    out = {}
+    for k, t in enumerate(fx):
+        ctx = R.RenderContext(70, 50, True)
+        ctx.set_color(0, 0, 0, 0)
+        ctx.draw_texture(t, 0, 0, 64, 48)
+        out[f"fx{k}"] = digest(ctx)["f64"]
+    return out
+
+
+def case_k5(R, image_rgba):
+    """Micro-cases of the quirks: exact pixel counts and values."""
+    out = {}
+    grad = np.zeros((4, 4, 4), dtype=np.uint8)
+    grad[..., 0] = np.arange(4)[None, :] * 60
+    grad[..., 3] = 255
+    g = R.Texture.from_numpy(grad)
+    for name, args in (("q2_frac_origin", (2.5, 2.5, 4, 4)), ("q4_last_texel", (0, 0, 4, 4))):
+        ctx = R.RenderContext(12, 12, True)
+        ctx.set_color(0, 0, 0, 0)
+        ctx.draw_texture(g, *args)
+        out[name] = digest(ctx)["f64"]
+    for name, rect in (("q3_rect_int", (2, 2, 4, 4)), ("q3_rect_frac", (2.5, 2.5, 4, 4))):
+        ctx = R.RenderContext(12, 12, True)
+        ctx.set_color(0, 0, 0, 0)
+        ctx.translate(0, 1e-3)   # force the transformed path for rects regardless
+        ctx.draw_rect(*rect, 1, 0, 0, 1)
+        buf = ctx.get_buffer_np().reshape(12, 12, 4)
+        out[name] = int((buf[..., 0] == 1).sum())
+    ctx = R.RenderContext(8, 8, True)   # quirk 1: scale(.25) and translate(-3,-3) are "no transform" for DrawTexture
+    ctx.set_color(0, 0, 0, 0)
+    ctx.scale(.25, .25)
+    ctx.translate(-3, -3)
+    ctx.draw_texture(g, 1, 1, 4, 4)
+    out["q1_ignored_matrix"] = digest(ctx)["f64"]
+    ctx = R.RenderContext(4, 4, True)   # quirk 5 + 8
+    ctx.set_color(.5, .5, .5, 1)
+    ctx.translate(0, 1e-3)
+    ctx.draw_rect(0, 0, 4, 4, 1, 0, 0, .25)
+    out["q5_alpha_overwrite"] = list(ctx.get_buffer_as_uint8()[16:20])   # pixel (0,1): (159, 95, 95, 63)
+    return out
+
+
+def case_k6(R, image_rgba):
+    ctx = R.RenderContext(320, 180, False)
+    streams.stream_k6(ctx, R.Texture.from_numpy(streams.k6_texture()))
+    return digest(ctx)
+
+
+# ---- randomised streams --------------------------------------------------------------------------
+RANDOM_SHAPES = [(97, 61, True), (64, 64, True), (130, 34, False), (16, 16, True), (257, 129, True), (48, 50, False)]
+
+
+def make_random_case(seed: int, use_apply_pixel: bool = False):
+    w, h, alpha = RANDOM_SHAPES[seed % len(RANDOM_SHAPES)]
+
+    def run(R, image_rgba):
+        ctx = R.RenderContext(w, h, alpha)
+        ctx.set_color(.2, .2, .2, .2)   # defined starting contents (the reference's are uninitialised)
+        tex = tiny_textures(R, image_rgba)
+        out = {}
+        for part in range(3):   # three flushes per context: later parts start from a non-trivial canvas
+            streams.stream_random(ctx, tex, seed * 10 + part, n=70, use_apply_pixel=use_apply_pixel)
+            out[f"part{part}"] = digest(ctx)
+        return out
+
+    return run
+
+
+def case_c2_small(R, image_rgba):
+    """C2's generator at 480x270 with 600 draws (finishes in seconds on the CPU)."""
+    ctx = R.RenderContext(480, 270, True)
+    tex = [R.Texture.from_numpy(t) for t in streams.make_c2_textures()]
+    streams.stream_c2(ctx, tex, n=600)
+    return digest(ctx)
+
+
+def case_c3_small(R, image_rgba):
+    ctx = R.RenderContext(512, 288, True)
+    atlas = R.Texture.from_numpy(streams.make_atlas(cells=4, cell=64))
+    streams.stream_c3(ctx, atlas, n=800, cells=4)
+    return digest(ctx)
+
+
+def case_c4_small(R, image_rgba):
+    """Two consecutive frames of the chart-shaped stream on a 480x270 RGB canvas."""
+    ctx = R.RenderContext(480, 270, False)
+    tex = [R.Texture.from_numpy(t) for t in streams.make_chart_textures()]
+    bg = R.Texture.from_numpy(streams.make_noise_texture(128, 7)).resample(480, 270)
+    out = {}
+    for f in (0, 37):
+        streams.stream_c4_frame(ctx, bg, tex, f, n_notes=120, n_fx=10)
+        out[f"frame{f}"] = digest(ctx)
+    return out
+
+
+def case_canvas_textures(R, image_rgba):
+    """CreateTextureFromRenderContext (deep copy) and f64 CreateTexture, drawn back."""
+    src = R.RenderContext(40, 30, True)
+    src.set_color(.1, .2, .3, .4)
+    src.translate(5, 5)
+    src.rotate(.3)
+    src.draw_rect(0, 0, 20, 10, 1, .5, .25, .75)
+    copy = src.as_texure()
+    src.set_color(1, 1, 1, 1)   # must not affect the copy
+    dst = R.RenderContext(64, 48, True)
+    dst.set_color(0, 0, 0, 1)
+    dst.translate(10, 4)
+    dst.rotate(-.2)
+    dst.draw_texture(copy, 0, 0, 50, 40)
+    vals = np.random.RandomState(5).rand(6, 7, 4)
+    ftex = R.Texture(7, 6, True, vals.tobytes(), is_uint8=False)
+    dst.draw_texture(ftex, 20, 10, 30, 30)
+    return digest(dst)
+
+
+def all_cases(reference_abi_only: bool = False):
+    cases = [("k1", case_k1), ("k2", case_k2), ("k3", case_k3), ("k4", case_k4), ("k5", case_k5), ("k6", case_k6),
+             ("c2_small", case_c2_small), ("c3_small", case_c3_small), ("c4_small", case_c4_small),
+             ("canvas_textures", case_canvas_textures)]
+    cases += [(f"random_{s}", make_random_case(s)) for s in range(18)]
+    if not reference_abi_only:
+        cases += [(f"random_ap_{s}", make_random_case(100 + s, use_apply_pixel=True)) for s in range(6)]
+    return cases

@@ -1,0 +1,46 @@
+"""Generates the committed parity fixtures from the UNMODIFIED reference build (oracle/_ref).
+
+Run in the build container (needs /root/reference and `make -C oracle ref`):
+
+    python tests/golden/make_golden.py
+
+Outputs (committed):
+  image_rgba.npz   raw RGBA of the reference's test_files/image.png (the only media file on the path)
+  golden.json      sha1 of the reference's u8 readback / f64 canvas for the streams in cases.py
+
+/root/reference does not exist on the GPU box, so the GPU tests compare against these files.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from libnativecpurenderer_b200.binding import Renderer  # noqa: E402
+import cases  # noqa: E402
+
+
+def main():
+    from PIL import Image
+
+    img = Image.open("/root/reference/test_files/image.png")
+    assert img.mode == "RGBA" and img.size == (128, 128)
+    rgba = np.frombuffer(img.tobytes(), dtype=np.uint8).reshape(128, 128, 4)
+    np.savez_compressed(os.path.join(HERE, "image_rgba.npz"), rgba=rgba)
+
+    ref = Renderer(os.path.join(ROOT, "oracle", "_ref", "libNativeCPURenderer.so"))
+    out = {}
+    for name, fn in cases.all_cases(reference_abi_only=True):
+        out[name] = fn(ref, rgba)
+        print(name, out[name])
+    with open(os.path.join(HERE, "golden.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()
