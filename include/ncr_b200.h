@@ -129,8 +129,9 @@ void NcrFreeHost(void* p);
  * records executed, or -1 on a malformed stream. */
 long NcrSubmitTrace(RenderContext* ctx, const void* trace, long bytes, Texture* const* textures, long n_textures);
 /* Re-execute the last flushed batch from its HBM-resident command buffers `iters` times (measurement: the
- * "inputs already resident" timing).  ms_out[iters] receives per-iteration device time from CUDA events on the
- * context's stream; flush_l2 != 0 overwrites a buffer larger than L2 before each iteration (outside the timed span). */
+ * "inputs already resident" timing).  ms_out[4*iters] receives, per iteration, CUDA-event times on the context's
+ * stream: {whole step, ncr_bin_coarse, ncr_bin_fine, ncr_composite}; flush_l2 != 0 overwrites a buffer larger than
+ * L2 before each iteration (outside the timed span). */
 int NcrRerunLastFlush(RenderContext* ctx, int iters, int flush_l2, float* ms_out);
 void NcrGetStats(RenderContext* ctx, NcrStats* out);
 void NcrSetStatsMode(RenderContext* ctx, int mode); /* bit 0: count blended pixels, bit 1: per-kernel events */

@@ -1088,14 +1088,18 @@ int NcrRerunLastFlush(RenderContext* ctx, int iters, int flush_l2, float* ms_out
     for (int it = 0; it < iters; ++it) {
         if (flush_l2) cudaMemsetAsync(g_l2_scrub, it & 0xff, kL2ScrubBytes, c->stream);
         cudaEventRecord(c->ev_t0, c->stream);
-        ncr_launch_flush(&c->last, c->stream, nullptr);
+        ncr_launch_flush(&c->last, c->stream, c->ev);
         cudaEventRecord(c->ev_t1, c->stream);
         g_launches += 3;
         c->stats.kernel_launches += 3;
         if (!CK(cudaStreamSynchronize(c->stream))) { c->failed = true; return -1; }
-        float ms = 0;
-        cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1);
-        if (ms_out) ms_out[it] = ms;
+        if (ms_out) {
+            float* o = ms_out + 4 * it;
+            cudaEventElapsedTime(&o[0], c->ev_t0, c->ev_t1);   // whole step: cursor reset + 3 kernels
+            cudaEventElapsedTime(&o[1], c->ev[0], c->ev[1]);   // ncr_bin_coarse
+            cudaEventElapsedTime(&o[2], c->ev[1], c->ev[2]);   // ncr_bin_fine
+            cudaEventElapsedTime(&o[3], c->ev[2], c->ev[3]);   // ncr_composite
+        }
     }
     c->u8_valid = c->last.u8_out != nullptr;
     return 0;
@@ -1202,6 +1206,7 @@ long NcrSubmitTrace(RenderContext* ctx, const void* trace, long bytes, Texture* 
 #undef NEED
         ++executed;
     }
+    if (p != end) return -1;   // trailing partial record
     return executed;
 }
 

@@ -145,7 +145,7 @@ class Replayer:
                                             ctypes.c_long, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p)
         self.lib.ncr_replay_run_threads.restype = ctypes.c_double
         self.lib.ncr_replay_run_threads.argtypes = (ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_int,
-                                                    ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_long, ctypes.c_int)
+                                                    ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_int)
         self.api = self.lib.ncr_replay_open(target_lib_path.encode())
         if not self.api:
             raise OSError(f"cannot bind {target_lib_path}")
@@ -159,10 +159,11 @@ class Replayer:
         return secs
 
     def run_threads(self, n_threads: int, width: int, height: int, alpha: bool, trace: np.ndarray, textures,
-                    repeats: int = 1) -> float:
+                    repeats: int = 1, warm_repeats: int = 0) -> float:
         table = texture_table(textures)
         secs = self.lib.ncr_replay_run_threads(self.api, n_threads, width, height, int(alpha),
-                                               ctypes.c_void_p(trace.ctypes.data), trace.nbytes, table, len(textures), repeats)
+                                               ctypes.c_void_p(trace.ctypes.data), trace.nbytes, table, len(textures), repeats,
+                                               warm_repeats)
         if secs < 0:
             raise ValueError("replay failed")
         return secs

@@ -1,0 +1,249 @@
+"""GPU suite: the CUDA path, driven through the C ABI, against (1) the committed digests of the unmodified
+reference build, (2) the C restatement run live on the same inputs, (3) size-independent properties at the
+benchmark's full sizes.  Bit-exact everywhere (RGBA8/RGB8 readback and the f64 canvas)."""
+import ctypes
+import hashlib
+
+import numpy as np
+import pytest
+
+import cases
+from libnativecpurenderer_b200 import streams, trace
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,fn", cases.all_cases(reference_abi_only=True), ids=lambda v: v if isinstance(v, str) else "")
+def test_product_matches_reference_golden(name, fn, gpu, golden, image_rgba):
+    assert fn(gpu, image_rgba) == golden[name]
+
+
+@pytest.mark.parametrize("name,fn", [c for c in cases.all_cases() if c[0].startswith("random_ap_")],
+                         ids=lambda v: v if isinstance(v, str) else "")
+def test_product_matches_port_with_apply_pixel(name, fn, gpu, port, image_rgba):
+    assert fn(gpu, image_rgba) == fn(port, image_rgba)
+
+
+@pytest.mark.parametrize("seed", range(300, 312))
+def test_product_matches_port_live(seed, gpu, port, image_rgba):
+    run = cases.make_random_case(seed)
+    assert run(gpu, image_rgba) == run(port, image_rgba)
+
+
+def test_product_matches_reference_live(gpu, ref, image_rgba):
+    for seed in range(400, 404):
+        run = cases.make_random_case(seed)
+        assert run(gpu, image_rgba) == run(ref, image_rgba)
+
+
+def test_state_machine_is_bit_identical(gpu, port):
+    import random
+
+    for seed in range(4):
+        outs = []
+        for R in (gpu, port):
+            rng = random.Random(seed)
+            ctx = R.RenderContext(8, 8, True)
+            for _ in range(60):
+                k = rng.random()
+                if k < .3:
+                    ctx.translate(rng.uniform(-50, 50), rng.uniform(-50, 50))
+                elif k < .6:
+                    ctx.rotate(rng.uniform(-10, 10))
+                elif k < .8:
+                    ctx.scale(rng.uniform(.1, 3), rng.uniform(.1, 3))
+                elif k < .9:
+                    ctx.save_state()
+                else:
+                    ctx.restore_state()
+            outs.append((ctx.get_transform(), ctx.get_inverse_transform()))
+        assert outs[0] == outs[1]
+    ctx = gpu.RenderContext(4, 4, True)
+    assert ctx.restore_state() is False   # cpp:293
+
+
+def test_trace_replay_equals_direct_calls(gpu, image_rgba):
+    """NcrSubmitTrace (one FFI crossing) and oracle/ncr_replay (C calls) render what per-call ctypes renders."""
+    from conftest import REPLAY_LIB
+
+    tex_np = streams.make_c2_textures()
+    tex = [gpu.Texture.from_numpy(t) for t in tex_np]
+    direct = gpu.RenderContext(480, 270, True)
+    streams.stream_c2(direct, tex, n=500)
+    want = cases.digest(direct)
+
+    rec = trace.TraceRecorder(480, 270, True)
+    streams.stream_c2(rec, [trace.TexSlot(k, t.shape[1], t.shape[0]) for k, t in enumerate(tex_np)], n=500)
+    arr = rec.as_array()
+    a = gpu.RenderContext(480, 270, True)
+    assert trace.submit_trace(a, arr, tex) == rec.n_records
+    assert cases.digest(a) == want
+    b = gpu.RenderContext(480, 270, True)
+    trace.Replayer(REPLAY_LIB, gpu.path).run(b, arr, tex)
+    assert cases.digest(b) == want
+
+
+def test_readback_paths_agree(gpu, image_rgba):
+    """GetBufferAsUInt8 fused into the composite, the standalone convert kernel, pinned and pageable destinations,
+    GetBuffer and GetColor all describe the same canvas."""
+    ctx = gpu.RenderContext(200, 120, False)
+    tex = cases.tiny_textures(gpu, image_rgba)
+    streams.stream_random(ctx, tex, 77, n=80)
+    fused = bytes(ctx.get_buffer_as_uint8())          # flush with fused u8
+    again = bytes(ctx.get_buffer_as_uint8())          # nothing pending: cached image
+    f64 = ctx.get_buffer_np()
+    ctx.flush()
+    ctx.draw_rect(0, 0, 1, 1, 0, 0, 0, 0)             # invalidates the cached image without changing a pixel
+    ctx.flush()
+    converted = bytes(ctx.get_buffer_as_uint8())      # standalone convert kernel
+    assert fused == again == converted
+    n = ctx.get_buffer_size()
+    pinned = gpu.lib.NcrAllocHost(n)
+    assert pinned
+    ctx.get_buffer_as_uint8_into(pinned)
+    assert ctypes.string_at(pinned, n) == fused
+    gpu.lib.NcrFreeHost(pinned)
+    scaled = f64 * 255
+    safe = np.where(np.abs(scaled) < 2 ** 31, scaled, 0)
+    assert (np.trunc(safe).astype(np.int64) & 0xFF).astype(np.uint8).tobytes() == fused
+    px = f64.reshape(120, 200, 3)
+    assert ctx.get_color(17.9, 5.2)[:3] == tuple(px[5, 17])
+    assert ctx.get_color(-3, 1e9)[:3] == tuple(px[119, 0])   # clamp, cpp:664-667
+
+
+def test_shared_canvas_texture_reads_the_canvas_as_of_the_draw(gpu, port, image_rgba):
+    outs = []
+    for R in (gpu, port):
+        src = R.RenderContext(32, 32, True)
+        src.set_color(.2, .4, .6, 1)
+        shared = src.as_texture_shared()
+        dst = R.RenderContext(64, 64, True)
+        dst.set_color(0, 0, 0, 1)
+        dst.translate(1, 1)
+        dst.rotate(.1)
+        src.draw_circle(16, 16, 10, 1, 0, 0, .5)          # pending on src when the alias is drawn
+        dst.draw_texture(shared, 0, 0, 40, 40)
+        src.set_color(1, 1, 1, 1)                          # later change must not leak into the recorded draw
+        dst.draw_texture(shared, 20, 20, 30, 30)
+        outs.append(cases.digest(dst))
+        assert (shared.width, shared.height) == (32, 32)
+    assert outs[0] == outs[1]
+
+
+def test_destroyed_texture_stays_valid_for_recorded_draws(gpu, port, image_rgba):
+    """The reference never frees (cpp:356-360), so Python may drop a texture right after drawing it."""
+    outs = []
+    for R in (gpu, port):
+        ctx = R.RenderContext(64, 64, True)
+        ctx.set_color(0, 0, 0, 1)
+        ctx.translate(3, 2)
+        ctx.rotate(.2)
+        t = R.Texture.from_numpy(image_rgba)
+        ctx.draw_texture(t, 0, 0, 50, 50)
+        del t
+        outs.append(cases.digest(ctx))
+    assert outs[0] == outs[1]
+
+
+def test_resize_discards_pixels_and_keeps_state(gpu):
+    ctx = gpu.RenderContext(16, 16, True)
+    ctx.translate(2, 3)
+    ctx.draw_rect(0, 0, 5, 5, 1, 1, 1, 1)
+    ctx.resize(24, 8)
+    assert ctx.get_buffer_size() == 24 * 8 * 4
+    assert ctx.get_transform() == (1, 0, 0, 1, 2, 3)
+    ctx.set_color(.5, .5, .5, .5)
+    assert set(ctx.get_buffer_as_uint8()) == {127}
+
+
+def test_empty_and_degenerate_inputs(gpu):
+    ctx = gpu.RenderContext(0, 0, True)
+    assert ctx.get_buffer_size() == 0 and bytes(ctx.get_buffer_as_uint8()) == b""
+    ctx = gpu.RenderContext(1, 1, False)
+    ctx.set_color(1, 0, 0, 1)
+    ctx.flush()
+    assert list(ctx.get_buffer_as_uint8()) == [255, 0, 0]
+    ctx = gpu.RenderContext(33, 17, True)   # nothing recorded: readback of the zero-initialised canvas
+    assert set(ctx.get_buffer_as_uint8()) == {0}
+    ctx.draw_rect(5, 5, -1, 4, 1, 1, 1, 1)   # early-outs (cpp:853)
+    ctx.draw_circle(5, 5, 0, 1, 1, 1, 1)
+    ctx.draw_line(1, 1, 1, 1, 3, 1, 1, 1, 1)
+    assert ctx.stats().n_cmds == 0
+    assert set(ctx.get_buffer_as_uint8()) == {0}
+
+
+# ---- full benchmark sizes: properties that do not need a CPU render -------------------------------------------
+def _c2_full(gpu, n=20000):
+    tex_np = streams.make_c2_textures()
+    tex = [gpu.Texture.from_numpy(t) for t in tex_np]
+    rec = trace.TraceRecorder(1920, 1080, True)
+    streams.stream_c2(rec, [trace.TexSlot(k, t.shape[1], t.shape[0]) for k, t in enumerate(tex_np)], n=n)
+    return tex, rec
+
+
+def test_c2_full_size_is_deterministic_and_flush_invariant(gpu):
+    """1080p, 20,000 draws: the image does not depend on how the stream is cut into flushes (one batch, or a flush
+    after every 997 records), nor on re-execution from the resident command buffers."""
+    tex, rec = _c2_full(gpu)
+    arr = rec.as_array()
+    one = gpu.RenderContext(1920, 1080, True)
+    trace.submit_trace(one, arr, tex)
+    want = hashlib.sha1(bytes(one.get_buffer_as_uint8())).hexdigest()
+    ms = (ctypes.c_float * 8)()
+    assert gpu.lib.NcrRerunLastFlush(one._ptr, 2, 1, ms) == 0
+    assert hashlib.sha1(bytes(one.get_buffer_as_uint8())).hexdigest() == want
+
+    # cut the same stream at record boundaries
+    raw = arr.tobytes()
+    offs, p, k = [0], 0, 0
+    while p < len(raw):
+        n = int.from_bytes(raw[p + 4:p + 8], "little")
+        p += 8 + 8 * n
+        k += 1
+        if k % 997 == 0:
+            offs.append(p)
+    offs.append(len(raw))
+    many = gpu.RenderContext(1920, 1080, True)
+    for a, b in zip(offs, offs[1:]):
+        if b > a:
+            piece = np.frombuffer(raw[a:b], dtype=np.uint8).copy()
+            buf = np.empty(len(piece) // 8 + 1, dtype=np.float64)
+            buf.view(np.uint8)[:len(piece)] = piece
+            trace.submit_trace(many, buf.view(np.uint8)[:len(piece)], tex)
+            many.flush()
+    assert hashlib.sha1(bytes(many.get_buffer_as_uint8())).hexdigest() == want
+
+
+def test_c2_full_size_matches_port(gpu, port):
+    """BASELINE config 2 at its full size (1080p RGBA, 20,000 mixed draws) against the C restatement, which needs
+    a few seconds of one host core for it: bit-exact u8 and f64."""
+    from conftest import REPLAY_LIB
+
+    tex_np = streams.make_c2_textures()
+    rec = trace.TraceRecorder(1920, 1080, True)
+    streams.stream_c2(rec, [trace.TexSlot(k, t.shape[1], t.shape[0]) for k, t in enumerate(tex_np)])
+    arr = rec.as_array()
+    got = []
+    for R in (gpu, port):
+        ctx = R.RenderContext(1920, 1080, True)
+        tex = [R.Texture.from_numpy(t) for t in tex_np]
+        trace.Replayer(REPLAY_LIB, R.path).run(ctx, arr, tex)
+        got.append(cases.digest(ctx))
+    assert got[0] == got[1]
+
+
+def test_c3_full_size_properties(gpu):
+    """4K, 50,000 atlas sprites: deterministic across runs and flush-invariant (the atlas is 16.8 MB of RGBA8)."""
+    atlas_np = streams.make_atlas()
+    atlas = gpu.Texture.from_numpy(atlas_np)
+    rec = trace.TraceRecorder(3840, 2160, True)
+    streams.stream_c3(rec, trace.TexSlot(0, 2048, 2048), n=50000)
+    arr = rec.as_array()
+    hashes = []
+    for _ in range(2):
+        ctx = gpu.RenderContext(3840, 2160, True)
+        trace.submit_trace(ctx, arr, [atlas])
+        hashes.append(hashlib.sha1(bytes(ctx.get_buffer_as_uint8())).hexdigest())
+        st = ctx.stats()
+        assert st.n_cmds > 40000 and st.fine_entries > st.n_cmds
+    assert hashes[0] == hashes[1]
