@@ -20,7 +20,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libNativeCPURenderer.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["api.cu", "kernels.cu", "host_misc.cpp"]
+SOURCES = ["api.cu", "kernels.cu", "composite.cu", "host_misc.cpp"]
 # -fmad=false: the reference's f64 expression trees must not be contracted into FMAs on the device;
 # -ffp-contract=off keeps the host-side per-call math (state.h) uncontracted as well.
 NVCC_FLAGS = [
@@ -52,8 +52,8 @@ def build_product(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(res.stdout + res.stderr)
         if res.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
-        if src == "kernels.cu":
-            with open(os.path.join(LIBDIR, "ptxas_kernels.log"), "w") as f:
+        if src.endswith(".cu") and src != "api.cu":
+            with open(os.path.join(LIBDIR, f"ptxas_{src[:-3]}.log"), "w") as f:
                 f.write(res.stderr)
         objs.append(obj)
     cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lpthread"]

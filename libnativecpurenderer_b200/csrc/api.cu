@@ -405,6 +405,7 @@ NcrCmd* begin_cmd(NcrContext* c, uint32_t op, i64 l, i64 r, i64 t, i64 b, bool c
     cmd->flags = flags;
     cmd->l = (int32_t)l; cmd->r = (int32_t)r; cmd->t = (int32_t)t; cmd->b = (int32_t)b;
     for (int k = 0; k < 4; ++k) cmd->ct[k] = c->st.ct[k];
+    if (c->st.ct[0] == 1.0 && c->st.ct[1] == 1.0 && c->st.ct[2] == 1.0) cmd->flags |= NCR_F_CT_RGB_ONE;
     NcrBox& bx = S.boxes.p[c->n];
     bx.l = cmd->l; bx.r = cmd->r; bx.t = cmd->t; bx.b = cmd->b;
     const unsigned long long tx = ((r - 1) / NCR_TILE) - (l / NCR_TILE) + 1, ty = ((b - 1) / NCR_TILE) - (t / NCR_TILE) + 1;
@@ -417,6 +418,20 @@ NcrCmd* begin_cmd(NcrContext* c, uint32_t op, i64 l, i64 r, i64 t, i64 b, bool c
 }
 
 void put_inverse(NcrContext* c, NcrCmd* cmd) { ncr_inverse(c->st.m, cmd->inv); }
+
+// Constant-colour primitives: everything ApplyPixel derives from the colour alone (cpp:525-536) is formed here, once,
+// with the same IEEE operations: p[0..3] = colour * colorTransform, p[4..6] = rgb * a, p[7] = 1 - a.
+void put_const_colour(NcrContext* c, NcrCmd* cmd, double r, double g, double b, double a) {
+    r *= c->st.ct[0];
+    g *= c->st.ct[1];
+    b *= c->st.ct[2];
+    a *= c->st.ct[3];
+    cmd->p[0] = r; cmd->p[1] = g; cmd->p[2] = b; cmd->p[3] = a;
+    cmd->p[4] = r * a; cmd->p[5] = g * a; cmd->p[6] = b * a;
+    cmd->p[7] = 1 - a;
+}
+
+bool is_pow2(i64 v) { return v > 0 && (v & (v - 1)) == 0; }
 
 // Texture operand of a draw.  Aliases of a canvas (cpp:377-384) are resolved to a snapshot of that canvas as of
 // this call, which is what an immediate-mode read of the shared buffer would have seen.
@@ -680,7 +695,7 @@ bool SetPixel(RenderContext* ctx, long x, long y, double r, double g, double b, 
         if (nx >= c->w) { nx = 0; ny = y + 1; }
         if (ny < c->h) {
             NcrCmd* spill = begin_cmd(c, NCR_OP_SET_PIXEL, nx, nx + 1, ny, ny + 1, false);
-            if (spill) { spill->p[0] = a; spill->p[4] = 1.0; }
+            if (spill) { spill->p[0] = a; spill->flags |= NCR_F_ONLY_RED; }
         }
     }
     return true;
@@ -691,7 +706,7 @@ bool ApplyPixel(RenderContext* ctx, long x, long y, double r, double g, double b
     if (!c) return false;
     if (x < 0 || x >= c->w || y < 0 || y >= c->h) return false;   // cpp:520-523
     NcrCmd* cmd = begin_cmd(c, NCR_OP_APPLY_PIXEL, x, x + 1, y, y + 1, false);
-    if (cmd) { cmd->p[0] = r; cmd->p[1] = g; cmd->p[2] = b; cmd->p[3] = a; }
+    if (cmd) put_const_colour(c, cmd, r, g, b, a);
     return true;
 }
 
@@ -714,7 +729,7 @@ void FillColor(RenderContext* ctx, double r, double g, double b, double a) {
     NcrContext* c = live(ctx);
     if (!c) return;
     NcrCmd* cmd = begin_cmd(c, NCR_OP_FILL_COLOR, 0, c->w, 0, c->h);
-    if (cmd) { cmd->p[0] = r; cmd->p[1] = g; cmd->p[2] = b; cmd->p[3] = a; }
+    if (cmd) put_const_colour(c, cmd, r, g, b, a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -724,6 +739,7 @@ static void fill_texture_fields(NcrContext* c, NcrCmd* cmd, const void* ptr, uin
     cmd->tex = ptr;
     cmd->flags |= tflags;
     if (c->sampling == 1) cmd->flags |= NCR_F_BILINEAR;
+    else if ((tflags & NCR_F_TEX_ALPHA) && !(tflags & NCR_F_TEX_F64) && tw * th < 0x7fffffffL) cmd->flags |= NCR_F_TEX_FAST;
     cmd->tex_w = (int32_t)tw;
     cmd->tex_h = (int32_t)th;
     keep_ref(c, keep);
@@ -791,6 +807,10 @@ void DrawSplittedTexture(RenderContext* ctx, Texture* tex_, double x, double y, 
     cmd->p[0] = uStart; cmd->p[1] = uEnd - uStart;
     cmd->p[2] = vStart; cmd->p[3] = vEnd - vStart;
     cmd->p[4] = (double)tw; cmd->p[5] = (double)th;
+    if (is_pow2(tw) && is_pow2(th)) {   // x / 2^k == x * 2^-k bit for bit
+        cmd->flags |= NCR_F_SPLIT_POW2;
+        cmd->p[6] = 1.0 / (double)tw; cmd->p[7] = 1.0 / (double)th;
+    }
 }
 
 void DrawRect(RenderContext* ctx, double x, double y, double width, double height, double r_, double g, double b_, double a) {
@@ -803,7 +823,7 @@ void DrawRect(RenderContext* ctx, double x, double y, double width, double heigh
     if (!cmd) return;
     put_inverse(c, cmd);
     cmd->x = x; cmd->y = y; cmd->xw = x + width; cmd->yh = y + height;
-    cmd->p[0] = r_; cmd->p[1] = g; cmd->p[2] = b_; cmd->p[3] = a;
+    put_const_colour(c, cmd, r_, g, b_, a);
 }
 
 void DrawVerticalGrd(RenderContext* ctx, double x, double y, double width, double height, double top_r, double top_g,
@@ -833,7 +853,7 @@ void DrawCircle(RenderContext* ctx, double x, double y, double radius, double r_
     if (!cmd) return;
     put_inverse(c, cmd);
     cmd->x = x; cmd->y = y; cmd->sx = radius;
-    cmd->p[0] = r_; cmd->p[1] = g; cmd->p[2] = b_; cmd->p[3] = a;
+    put_const_colour(c, cmd, r_, g, b_, a);
 }
 
 // Polygon fill in inverse-mapped space (cpp:908-916).  The reference scans the whole canvas; the recorded box is
@@ -875,7 +895,7 @@ static void record_polygon(NcrContext* c, const double* pts, size_t n, double r_
     cmd->aux_n = (uint32_t)n;
     memcpy(S.aux.p + c->n_aux, pts, 2 * n * sizeof(double));
     c->n_aux += 2 * n;
-    cmd->p[0] = r_; cmd->p[1] = g; cmd->p[2] = b_; cmd->p[3] = a;
+    put_const_colour(c, cmd, r_, g, b_, a);
 }
 
 void DrawLine(RenderContext* ctx, double x1, double y1, double x2, double y2, double width, double r, double g, double b,

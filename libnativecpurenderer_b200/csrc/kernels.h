@@ -13,6 +13,7 @@ extern "C" {
 // memset cursors, bin (coarse, fine), composite — all on stream s.  ev: 4 events recorded around the
 // three kernels (timing mode) or nullptr.
 void ncr_launch_flush(const NcrFlushArgs* A, cudaStream_t s, cudaEvent_t* ev);
+void ncr_launch_composite(const NcrFlushArgs* A, cudaStream_t s);
 void ncr_launch_convert_u8(const double* fb, unsigned char* out, size_t n, cudaStream_t s);
 void ncr_launch_resample(const NcrCmd* src, void* out, int ow, int oh, cudaStream_t s);
 }

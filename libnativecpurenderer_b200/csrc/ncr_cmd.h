@@ -32,7 +32,11 @@ enum : uint32_t {
     NCR_F_TEX_F64 = 1u << 1,      // texels are f64 (else u8 decoded through the k/255.0 table)
     NCR_F_BILINEAR = 1u << 2,     // extension (parity unpinned): cpp:575-620 formula
     NCR_F_CLIP = 1u << 3,         // extension: box already intersected with the clip rect on the host
-    NCR_F_RGB_SPILL = 1u << 4,    // SetPixel/SetColor on a 3-channel canvas: alpha lands in the next element (cpp:510)
+    NCR_F_RGB_SPILL = 1u << 4,    // SetColor on a 3-channel canvas, non-uniform colour: alpha lands in the next element (cpp:510)
+    NCR_F_ONLY_RED = 1u << 5,     // SET_PIXEL that writes only the red element (the cpp:510 spill of the previous pixel)
+    NCR_F_CT_RGB_ONE = 1u << 6,   // ct[0..2] are all exactly 1.0: v * 1.0 == v, the multiplies are skipped
+    NCR_F_SPLIT_POW2 = 1u << 7,   // TEX_SPLIT: texture width and height are powers of two; p[6], p[7] = 1/w, 1/h (exact)
+    NCR_F_TEX_FAST = 1u << 8,     // RGBA8 texels, nearest sampling, fewer than 2^31 texels: inlined sampler
 };
 
 struct alignas(16) NcrCmd {
@@ -80,7 +84,8 @@ struct NcrFlushArgs {
     uint32_t* coarse_off;       // [bins] offset, [bins] count
     uint32_t* fine_list;        // capacity fine_cap
     uint32_t* fine_off;         // [tiles] offset, [tiles] count
-    uint32_t* cursors;          // [0] coarse cursor, [1] fine cursor, [2..3] blended-pixel counter (u64)
+    uint32_t* cursors;          // [0] coarse cursor, [1] fine cursor, [2..3] blended-pixel counter (u64), [4] overflow flag,
+                                // [5] composite work counter (half-tiles handed out)
     uint32_t coarse_cap, fine_cap;
     uint32_t count_pixels;      // stats mode: count APPLY executions
 };
