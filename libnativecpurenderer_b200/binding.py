@@ -117,6 +117,9 @@ class NcrStats(ctypes.Structure):
 
 
 def default_library_path() -> str:
+    override = os.environ.get("NCR_LIBRARY")   # A/B builds of the product during development
+    if override:
+        return override
     here = os.path.dirname(os.path.abspath(__file__))
     return os.path.join(here, "lib", "libNativeCPURenderer.so")
 

@@ -38,6 +38,31 @@ def _newer(target: str, deps: list[str]) -> bool:
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
+def build_variant(name: str, defines: list[str]) -> str:
+    """Development helper: the product compiled with extra -D flags into lib/variants/<name>/ (for A/B timing)."""
+    out_dir = os.path.join(LIBDIR, "variants", name)
+    os.makedirs(out_dir, exist_ok=True)
+    objs = []
+    for src in SOURCES:
+        obj = os.path.join(out_dir, src.rsplit(".", 1)[0] + ".o")
+        cmd = [NVCC, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError(f"nvcc failed on {src}")
+        if src == "composite.cu":
+            with open(os.path.join(out_dir, "ptxas_composite.log"), "w") as f:
+                f.write(res.stderr)
+        objs.append(obj)
+    lib = os.path.join(out_dir, "libNativeCPURenderer.so")
+    res = subprocess.run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib, *objs, "-lpthread"],
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("link failed")
+    return lib
+
+
 def build_product(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "ncr_b200.h"), __file__]

@@ -24,6 +24,9 @@
 #define FULL 0xffffffffu
 #define NCR_LUT_COPIES 16
 #define NCR_COMPOSITE_THREADS 128
+#ifndef NCR_COMPOSITE_MIN_CTAS
+#define NCR_COMPOSITE_MIN_CTAS 3
+#endif
 
 namespace {
 
@@ -108,36 +111,344 @@ __device__ __forceinline__ bool point_in_poly(const double* __restrict__ pts, ui
     return res;
 }
 
-// ApplyPixel's blend for an already colour-transformed source (reference cpp:533-546).
+// ApplyPixel's blend for an already colour-transformed source (reference cpp:533-546), applied under the per-lane
+// predicate `in` as selects (no branch, so the four pixel slots of a lane interleave):
+//     if (a != 1) c = dst*(1 - a) + c*a;   dst.rgb = c;   dst.a = a (canvas with alpha)
+// Lanes with a == 1 (plain store, cpp:533 skips the blend) are NOT handled here: the caller collects them in `opaque`
+// and applies store_opaque() under one warp-uniform branch, because they are rare.
 template <bool ALPHA>
-__device__ __forceinline__ void blend(double& dr, double& dg, double& db, double& da, double r, double g, double b, double a) {
-    if (a != 1.0) {
-        const double om = SUB(1.0, a);
-        r = ADD(MUL(dr, om), MUL(r, a));
-        g = ADD(MUL(dg, om), MUL(g, a));
-        b = ADD(MUL(db, om), MUL(b, a));
-    }
-    dr = r; dg = g; db = b;
-    if (ALPHA) da = a;   // source alpha replaces destination alpha (cpp:544)
+__device__ __forceinline__ bool blend(double& dr, double& dg, double& db, double& da, double r, double g, double b, double a,
+                                      bool in) {
+    const bool blended = in && (a != 1.0);   // true for NaN, as in C
+    const double om = SUB(1.0, a);
+    const double nr = ADD(MUL(dr, om), MUL(r, a));
+    const double ng = ADD(MUL(dg, om), MUL(g, a));
+    const double nb = ADD(MUL(db, om), MUL(b, a));
+    dr = blended ? nr : dr;
+    dg = blended ? ng : dg;
+    db = blended ? nb : db;
+    if (ALPHA) da = in ? a : da;   // source alpha replaces destination alpha (cpp:544)
+    return in && !(a != 1.0);
+}
+
+__device__ __forceinline__ void store_opaque(double& dr, double& dg, double& db, double r, double g, double b, bool opaque) {
+    dr = opaque ? r : dr;
+    dg = opaque ? g : dg;
+    db = opaque ? b : db;
+}
+
+// Constant-colour blend (cpp:533-546 with the colour-only subexpressions formed on the host): dst = dst*om + q.
+__device__ __forceinline__ void blend_const(double& dr, double& dg, double& db, double om, double q0, double q1, double q2,
+                                            bool in) {
+    const double nr = ADD(MUL(dr, om), q0), ng = ADD(MUL(dg, om), q1), nb = ADD(MUL(db, om), q2);
+    dr = in ? nr : dr;
+    dg = in ? ng : dg;
+    db = in ? nb : db;
+}
+
+__device__ __forceinline__ void store_pred(double& d, double v, bool in) { d = in ? v : d; }
+
+// u8 -> k/255.0 through the replicated table: byte k of the packed texel, copy (lane & 15).  `base` is the shared-space
+// byte address of this lane's copy of entry 0; entries are 128 B apart.
+template <int K>
+__device__ __forceinline__ double lut_byte(uint32_t base, uint32_t texel) {
+    const uint32_t k = __byte_perm(texel, 0, 0x4440 + K);
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + k * 128u));
+    return v;
 }
 
 #define FOR4 _Pragma("unroll") for (int p = 0; p < 4; ++p)
 
+// Per-lane pixel slots of the current half-tile.
+struct Slots {
+    int xs[2], ys[2];        // pixel columns / rows owned by this lane
+    double fx[2], fy[2];     // the same as f64 (int -> f64 is exact)
+};
+
+// Shared tail of the textured ops: decode four RGBA8 texels and blend (straight-line, predicated).  RGB_ONE: the colour
+// transform's rgb are exactly 1.0, so r * 1.0 (cpp:525-527) is the identity and is not issued.
+template <bool ALPHA, bool COUNT, bool RGB_ONE>
+__device__ __forceinline__ void shade_rgba8(const NcrCmd& c, uint32_t lut_base, const uint32_t (&tx)[4], const bool (&in)[4],
+                                            double (&dr)[4], double (&dg)[4], double (&db)[4], double (&da)[4],
+                                            unsigned long long& n_applied) {
+    const double ct3 = c.ct[3];
+    double ct0 = 1.0, ct1 = 1.0, ct2 = 1.0;
+    if (!RGB_ONE) { ct0 = c.ct[0]; ct1 = c.ct[1]; ct2 = c.ct[2]; }
+    bool opaque[4];
+    FOR4 {
+        const uint32_t t = tx[p];
+        double r = lut_byte<0>(lut_base, t), g = lut_byte<1>(lut_base, t), b = lut_byte<2>(lut_base, t);
+        double a = lut_byte<3>(lut_base, t);
+        if (!RGB_ONE) { r = MUL(r, ct0); g = MUL(g, ct1); b = MUL(b, ct2); }   // cpp:525-527
+        a = MUL(a, ct3);                                                       // cpp:528
+        opaque[p] = blend<ALPHA>(dr[p], dg[p], db[p], da[p], r, g, b, a, in[p]);
+        if (COUNT) n_applied += in[p] ? 1 : 0;
+    }
+    if (__any_sync(FULL, opaque[0] || opaque[1] || opaque[2] || opaque[3])) {   // a == 1: the source is stored as is
+        FOR4 {
+            const uint32_t t = tx[p];
+            double r = lut_byte<0>(lut_base, t), g = lut_byte<1>(lut_base, t), b = lut_byte<2>(lut_base, t);
+            if (!RGB_ONE) { r = MUL(r, ct0); g = MUL(g, ct1); b = MUL(b, ct2); }
+            store_opaque(dr[p], dg[p], db[p], r, g, b, opaque[p]);
+        }
+    }
+}
+
+// Fast path of the two hot ops — DrawTexture (inverse-mapped, cpp:753-778) and DrawSplittedTexture (cpp:781-820) on
+// RGBA8 textures with nearest sampling.  Written as straight-line code over the four pixel slots (no branch between
+// slots), so the f64 dependency chains of the slots interleave.
 template <bool ALPHA, bool COUNT>
-__global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, 4) ncr_composite(NcrFlushArgs A) {
+__device__ __forceinline__ void tex_fast(const NcrCmd& c, const uint32_t op, const uint32_t flags, const Slots& S,
+                                         const double* lut, uint32_t lut_base, bool (&in)[4], double (&dr)[4], double (&dg)[4],
+                                         double (&db)[4], double (&da)[4], unsigned long long& n_applied) {
+    // TransformPointFromMatrix(inv, i, j), cpp:451-452: (inv0*i + inv2*j) + inv4.  inv0*i depends only on the pixel
+    // column and inv2*j only on the row: each product is formed once per lane.
+    const double i0 = c.inv[0], i1 = c.inv[1], i2 = c.inv[2], i3 = c.inv[3], i4 = c.inv[4], i5 = c.inv[5];
+    const double ax[2] = {MUL(i0, S.fx[0]), MUL(i0, S.fx[1])}, bx[2] = {MUL(i1, S.fx[0]), MUL(i1, S.fx[1])};
+    const double ay[2] = {MUL(i2, S.fy[0]), MUL(i2, S.fy[1])}, by[2] = {MUL(i3, S.fy[0]), MUL(i3, S.fy[1])};
+    const double cx = c.x, cy = c.y, cxw = c.xw, cyh = c.yh, sx = c.sx, sy = c.sy;
+    double u[4], v[4];
+    FOR4 {
+        const double X = ADD(ADD(ax[p & 1], ay[p >> 1]), i4);
+        const double Y = ADD(ADD(bx[p & 1], by[p >> 1]), i5);
+        // the four inclusive bounds, cpp:765-768 (NaN compares false on both sides, as in C)
+        in[p] = in[p] && !(X < cx) && !(X > cxw) && !(Y < cy) && !(Y > cyh);
+        u[p] = MUL(SUB(X, cx), sx);   // cpp:770-771
+        v[p] = MUL(SUB(Y, cy), sy);
+    }
+    if (!__any_sync(FULL, in[0] || in[1] || in[2] || in[3])) return;
+    if (op == NCR_OP_TEX_SPLIT) {
+        // cpp:812-813: u = (uStart + (uEnd - uStart) * u / tex->width) * tex->width
+        const double uS = c.p[0], dU = c.p[1], vS = c.p[2], dV = c.p[3], fw = c.p[4], fh = c.p[5];
+        if (flags & NCR_F_SPLIT_POW2) {
+            // width and height are powers of two: x / 2^k and x * 2^-k are the same correctly rounded value
+            const double rw = c.p[6], rh = c.p[7];
+            FOR4 {
+                u[p] = MUL(ADD(uS, MUL(MUL(dU, u[p]), rw)), fw);
+                v[p] = MUL(ADD(vS, MUL(MUL(dV, v[p]), rh)), fh);
+            }
+        } else {
+            FOR4 {
+                u[p] = MUL(ADD(uS, DIV(MUL(dU, u[p]), fw)), fw);
+                v[p] = MUL(ADD(vS, DIV(MUL(dV, v[p]), fh)), fh);
+            }
+        }
+    }
+    // InterpolateColorFromBuffer, cpp:560-566: clamp u<0 -> 0, u >= w-1 -> w-2, then (i64) truncation.  Done after the
+    // truncation here, which is the same function: trunc(u) <= 0 iff u < 1, and because w-1 is an integer,
+    // u >= w-1 iff trunc(u) >= w-1 (cvt.rzi saturates, so huge u stays >= w-1).
+    const int tw = c.tex_w, th = c.tex_h;
+    const uint32_t* t32 = (const uint32_t*)c.tex;
+    uint32_t tx[4];
+    FOR4 {
+        int xi = __double2int_rz(u[p]), yi = __double2int_rz(v[p]);
+        xi = xi >= tw - 1 ? tw - 2 : xi;
+        yi = yi >= th - 1 ? th - 2 : yi;
+        xi = max(xi, 0);   // also keeps 1-texel-wide textures in bounds (the reference reads out of bounds there)
+        yi = max(yi, 0);
+        tx[p] = in[p] ? __ldg(t32 + (yi * tw + xi)) : 0u;
+    }
+    if (flags & NCR_F_CT_RGB_ONE) shade_rgba8<ALPHA, COUNT, true>(c, lut_base, tx, in, dr, dg, db, da, n_applied);
+    else shade_rgba8<ALPHA, COUNT, false>(c, lut_base, tx, in, dr, dg, db, da, n_applied);
+}
+
+// One command applied to the warp's 128 pixels.  `c` lives in shared memory (warp-uniform reads: one wavefront each).
+template <bool ALPHA, bool COUNT>
+__device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A, const Slots& S, const double* lut /* + lane&15 */, uint32_t lut_base,
+                                          double (&dr)[4], double (&dg)[4], double (&db)[4], double (&da)[4],
+                                          unsigned long long& n_applied) {
+    const uint32_t op = c.op, flags = c.flags;
+    // pixel-box membership: the reference's loop bounds (boxes are clamped to the canvas on the host, so a pixel slot
+    // outside the canvas is never inside a box).  (unsigned)(v - lo) < (unsigned)(hi - lo)  <=>  lo <= v < hi.
+    const unsigned wx = (unsigned)(c.r - c.l), wy = (unsigned)(c.b - c.t);
+    const bool inx[2] = {(unsigned)(S.xs[0] - c.l) < wx, (unsigned)(S.xs[1] - c.l) < wx};
+    const bool iny[2] = {(unsigned)(S.ys[0] - c.t) < wy, (unsigned)(S.ys[1] - c.t) < wy};
+    bool in[4];
+    FOR4 in[p] = inx[p & 1] && iny[p >> 1];
+
+    if (op == NCR_OP_SET_COLOR) {   // cpp:643-657
+        FOR4 if (in[p]) {
+            dr[p] = c.p[0]; dg[p] = c.p[1]; db[p] = c.p[2];
+            if (ALPHA) da[p] = c.p[3];
+            // 3-channel canvas, non-uniform colour: SetPixel's index+3 store (cpp:510) leaves `a` in the red of pixel
+            // (0, j>=1), because column 0 is written first and the last column of the previous row spills into it.
+            else if ((flags & NCR_F_RGB_SPILL) && S.xs[p & 1] == 0 && S.ys[p >> 1] >= 1 && A.d.w > 1) dr[p] = c.p[3];
+        }
+        return;
+    }
+    if (op == NCR_OP_SET_PIXEL) {   // cpp:494-513
+        FOR4 if (in[p]) {
+            dr[p] = c.p[0];
+            if (!(flags & NCR_F_ONLY_RED)) {
+                dg[p] = c.p[1]; db[p] = c.p[2];
+                if (ALPHA) da[p] = c.p[3];
+            }
+        }
+        return;
+    }
+
+    if ((op == NCR_OP_TEX || op == NCR_OP_TEX_SPLIT) && (flags & NCR_F_TEX_FAST)) {
+        tex_fast<ALPHA, COUNT>(c, op, flags, S, lut, lut_base, in, dr, dg, db, da, n_applied);
+        return;
+    }
+
+    // inverse-mapped source position, TransformPointFromMatrix(inv, i, j), cpp:451-452: (inv0*i + inv2*j) + inv4.
+    double X[4], Y[4];
+    if (op != NCR_OP_FILL_COLOR && op != NCR_OP_APPLY_PIXEL && op != NCR_OP_TEX_IDENT && op != NCR_OP_TEX_PERSP) {
+        const double ax[2] = {MUL(c.inv[0], S.fx[0]), MUL(c.inv[0], S.fx[1])}, bx[2] = {MUL(c.inv[1], S.fx[0]), MUL(c.inv[1], S.fx[1])};
+        const double ay[2] = {MUL(c.inv[2], S.fy[0]), MUL(c.inv[2], S.fy[1])}, by[2] = {MUL(c.inv[3], S.fy[0]), MUL(c.inv[3], S.fy[1])};
+        const double i4 = c.inv[4], i5 = c.inv[5];
+        FOR4 {
+            X[p] = ADD(ADD(ax[p & 1], ay[p >> 1]), i4);
+            Y[p] = ADD(ADD(bx[p & 1], by[p >> 1]), i5);
+        }
+        if (op != NCR_OP_CIRCLE && op != NCR_OP_POLY) {
+            // the four inclusive bounds, cpp:765-768 (NaN compares false on both sides, as in C)
+            const double cx = c.x, cy = c.y, cxw = c.xw, cyh = c.yh;
+            FOR4 in[p] = in[p] && !(X[p] < cx) && !(X[p] > cxw) && !(Y[p] < cy) && !(Y[p] > cyh);
+        }
+    }
+
+    if (op == NCR_OP_GRAD) {   // cpp:1308-1313; p[4..7] = bottom - top
+        const double hgt = c.sy, cy = c.y;
+        if (!__any_sync(FULL, in[0] || in[1] || in[2] || in[3])) return;
+        FOR4 {
+            const double t = DIV(SUB(Y[p], cy), hgt);
+            const double r = MUL(ADD(c.p[0], MUL(c.p[4], t)), c.ct[0]);
+            const double g = MUL(ADD(c.p[1], MUL(c.p[5], t)), c.ct[1]);
+            const double b = MUL(ADD(c.p[2], MUL(c.p[6], t)), c.ct[2]);
+            const double a = MUL(ADD(c.p[3], MUL(c.p[7], t)), c.ct[3]);
+            const bool opq = blend<ALPHA>(dr[p], dg[p], db[p], da[p], r, g, b, a, in[p]);
+            store_opaque(dr[p], dg[p], db[p], r, g, b, opq);
+            if (COUNT) n_applied += in[p] ? 1 : 0;
+        }
+        return;
+    }
+
+    if (op == NCR_OP_RECT || op == NCR_OP_CIRCLE || op == NCR_OP_POLY || op == NCR_OP_FILL_COLOR || op == NCR_OP_APPLY_PIXEL) {
+        if (op == NCR_OP_CIRCLE) {   // cpp:939-943
+            const double cx = c.x, cy = c.y, rad = c.sx;
+            FOR4 if (__any_sync(FULL, in[p])) {
+                const double ddx = SUB(X[p], cx), ddy = SUB(Y[p], cy);
+                const double dist = __dsqrt_rn(ADD(MUL(ddx, ddx), MUL(ddy, ddy)));
+                in[p] = in[p] && !(dist > rad);
+            }
+        } else if (op == NCR_OP_POLY) {   // cpp:913
+            const double* pts = A.aux + c.aux_off;
+            const uint32_t npts = c.aux_n;
+            FOR4 if (__any_sync(FULL, in[p])) in[p] = in[p] && point_in_poly(pts, npts, X[p], Y[p]);
+        }
+        // constant colour: p[0..3] = colour * ct, p[4..6] = rgb*a, p[7] = 1-a, formed on the host with the same IEEE
+        // operations ApplyPixel performs per pixel (cpp:525-536).
+        const double sa = c.p[3];
+        if (sa != 1.0) {
+            const double q0 = c.p[4], q1 = c.p[5], q2 = c.p[6], om = c.p[7];
+            FOR4 {
+                blend_const(dr[p], dg[p], db[p], om, q0, q1, q2, in[p]);
+                if (ALPHA) store_pred(da[p], sa, in[p]);
+                if (COUNT) n_applied += in[p] ? 1 : 0;
+            }
+        } else {
+            const double c0 = c.p[0], c1 = c.p[1], c2 = c.p[2];
+            FOR4 {
+                store_pred(dr[p], c0, in[p]); store_pred(dg[p], c1, in[p]); store_pred(db[p], c2, in[p]);
+                if (ALPHA) store_pred(da[p], sa, in[p]);
+                if (COUNT) n_applied += in[p] ? 1 : 0;
+            }
+        }
+        return;
+    }
+
+    // ---- textured ops: DrawTexture (both paths), DrawSplittedTexture, perspective extension ----
+    const int tw = c.tex_w, th = c.tex_h;
+    double u[4], v[4];
+    if (op == NCR_OP_TEX_IDENT) {   // cpp:741-745: pixels i >= (i64)x with (f64)i < x + width; u = (i - x) * scaleX
+        FOR4 {
+            const double fi = S.fx[p & 1], fj = S.fy[p >> 1];
+            in[p] = in[p] && fi >= c.p[0] && fi < c.xw && fj >= c.p[1] && fj < c.yh;
+            u[p] = MUL(SUB(fi, c.x), c.sx);
+            v[p] = MUL(SUB(fj, c.y), c.sy);
+        }
+    } else if (op == NCR_OP_TEX_PERSP) {   // extension: row-major 3x3 inverse homography, then cpp:765-771
+        FOR4 {
+            const double fi = S.fx[p & 1], fj = S.fy[p >> 1];
+            const double hw = ADD(ADD(MUL(c.p[0], fi), MUL(c.p[1], fj)), c.p[2]);
+            const double Xp = DIV(ADD(ADD(MUL(c.inv[0], fi), MUL(c.inv[1], fj)), c.inv[2]), hw);
+            const double Yp = DIV(ADD(ADD(MUL(c.inv[3], fi), MUL(c.inv[4], fj)), c.inv[5]), hw);
+            in[p] = in[p] && hw > 0.0 && !(Xp < c.x) && !(Xp > c.xw) && !(Yp < c.y) && !(Yp > c.yh);
+            u[p] = MUL(SUB(Xp, c.x), c.sx);
+            v[p] = MUL(SUB(Yp, c.y), c.sy);
+        }
+    } else {   // NCR_OP_TEX / NCR_OP_TEX_SPLIT, cpp:770-771
+        const double cx = c.x, cy = c.y, sx = c.sx, sy = c.sy;
+        FOR4 {
+            u[p] = MUL(SUB(X[p], cx), sx);
+            v[p] = MUL(SUB(Y[p], cy), sy);
+        }
+        if (op == NCR_OP_TEX_SPLIT) {
+            // cpp:812-813: u = (uStart + (uEnd - uStart) * u / tex->width) * tex->width
+            const double uS = c.p[0], dU = c.p[1], vS = c.p[2], dV = c.p[3], fw = c.p[4], fh = c.p[5];
+            if (flags & NCR_F_SPLIT_POW2) {
+                // width and height are powers of two: x / 2^k and x * 2^-k are the same correctly rounded value
+                const double rw = c.p[6], rh = c.p[7];
+                FOR4 {
+                    u[p] = MUL(ADD(uS, MUL(MUL(dU, u[p]), rw)), fw);
+                    v[p] = MUL(ADD(vS, MUL(MUL(dV, v[p]), rh)), fh);
+                }
+            } else {
+                FOR4 if (__any_sync(FULL, in[p])) {
+                    u[p] = MUL(ADD(uS, DIV(MUL(dU, u[p]), fw)), fw);
+                    v[p] = MUL(ADD(vS, DIV(MUL(dV, v[p]), fh)), fh);
+                }
+            }
+        }
+    }
+
+    if (flags & NCR_F_TEX_FAST) {   // RGBA8 texels, nearest, < 2^31 texels (clamp-after-truncate: see tex_fast)
+        const uint32_t* t32 = (const uint32_t*)c.tex;
+        uint32_t tx[4];
+        FOR4 {
+            int xi = __double2int_rz(u[p]), yi = __double2int_rz(v[p]);
+            xi = xi >= tw - 1 ? tw - 2 : xi;
+            yi = yi >= th - 1 ? th - 2 : yi;
+            xi = max(xi, 0);
+            yi = max(yi, 0);
+            tx[p] = in[p] ? __ldg(t32 + (yi * tw + xi)) : 0u;
+        }
+        if (flags & NCR_F_CT_RGB_ONE) shade_rgba8<ALPHA, COUNT, true>(c, lut_base, tx, in, dr, dg, db, da, n_applied);
+        else shade_rgba8<ALPHA, COUNT, false>(c, lut_base, tx, in, dr, dg, db, da, n_applied);
+    } else {
+        FOR4 if (in[p]) {
+            double s[4];
+            sample_slow(c.tex, flags, tw, th, lut - (threadIdx.x & 15), threadIdx.x & 15, u[p], v[p], s);
+            const double r = MUL(s[0], c.ct[0]), g = MUL(s[1], c.ct[1]), b = MUL(s[2], c.ct[2]), a = MUL(s[3], c.ct[3]);
+            const bool opq = blend<ALPHA>(dr[p], dg[p], db[p], da[p], r, g, b, a, true);
+            store_opaque(dr[p], dg[p], db[p], r, g, b, opq);
+            if (COUNT) ++n_applied;
+        }
+    }
+}
+
+template <bool ALPHA, bool COUNT>
+__global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, NCR_COMPOSITE_MIN_CTAS) ncr_composite(NcrFlushArgs A) {
     // u8 / 255.0 (CreateTextureUInt8, cpp:350), IEEE division on both sides.  16 copies, copy c of entry k at
     // [k*16 + c]: a lane only ever reads copy (lane & 15), so the 64-bit lookups of a half-warp never collide on a bank.
     __shared__ double s_lut[256 * NCR_LUT_COPIES];
+    // Per-warp double-buffered command slot: the next command of the list is fetched while the current one is applied.
+    __shared__ NcrCmd s_cmd[NCR_COMPOSITE_THREADS / 32][2];
     for (int e = threadIdx.x; e < 256 * NCR_LUT_COPIES; e += NCR_COMPOSITE_THREADS)
         s_lut[e] = DIV((double)(e >> 4), 255.0);
     __syncthreads();
 
-    const int lane = threadIdx.x & 31;
-    const int l16 = lane & 15;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double* lut = s_lut + (lane & 15);
+    const uint32_t lut_base = (uint32_t)__cvta_generic_to_shared(lut);
     const int lx = lane & 7, ly = lane >> 3;
     const int n_tiles = A.d.tiles_x * A.d.tiles_y;
     const int n_tasks = n_tiles * 2;
     constexpr int IPP = ALPHA ? 4 : 3;
+    constexpr uint32_t WORDS = NCR_CMD_WORDS16;   // 15 x 16 B
     const int W = A.d.w, H = A.d.h;
     unsigned long long n_applied = 0;
 
@@ -154,19 +465,20 @@ __global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, 4) ncr_composite(NcrFlu
         const int x0 = (tile % A.d.tiles_x) * NCR_TILE;
         const int y0 = (tile / A.d.tiles_x) * NCR_TILE + (task & 1) * 8;
         if (y0 >= H) continue;
-        const int xs[2] = {x0 + lx, x0 + 8 + lx};
-        const int ys[2] = {y0 + ly, y0 + 4 + ly};
-        const double fx[2] = {(double)xs[0], (double)xs[1]};
-        const double fy[2] = {(double)ys[0], (double)ys[1]};
+        Slots S;
+        S.xs[0] = x0 + lx; S.xs[1] = x0 + 8 + lx;
+        S.ys[0] = y0 + ly; S.ys[1] = y0 + 4 + ly;
+        S.fx[0] = (double)S.xs[0]; S.fx[1] = (double)S.xs[1];
+        S.fy[0] = (double)S.ys[0]; S.fy[1] = (double)S.ys[1];
         bool valid[4];
-        FOR4 valid[p] = xs[p & 1] < W && ys[p >> 1] < H;
+        FOR4 valid[p] = S.xs[p & 1] < W && S.ys[p >> 1] < H;
 
         double dr[4], dg[4], db[4], da[4];
         FOR4 { dr[p] = 0.0; dg[p] = 0.0; db[p] = 0.0; da[p] = 0.0; }
         // The canvas is read unless the list starts with a SetColor (then every pixel is overwritten first).
         if (A.load_fb != 0 || lcount == 0) {
             FOR4 if (valid[p]) {
-                const double* q = A.fb + ((size_t)ys[p >> 1] * W + xs[p & 1]) * IPP;
+                const double* q = A.fb + ((size_t)S.ys[p >> 1] * W + S.xs[p & 1]) * IPP;
                 if (ALPHA) {
                     const double2 lo = ((const double2*)q)[0], hi = ((const double2*)q)[1];
                     dr[p] = lo.x; dg[p] = lo.y; db[p] = hi.x; da[p] = hi.y;
@@ -176,234 +488,46 @@ __global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, 4) ncr_composite(NcrFlu
             }
         }
 
-        for (uint32_t k0 = 0; k0 < lcount; k0 += 32) {
-            const uint32_t mine = (k0 + lane < lcount) ? __ldg(&A.fine_list[loff + k0 + lane]) : 0u;
-            const uint32_t nk = min(32u, lcount - k0);
-            for (uint32_t kk = 0; kk < nk; ++kk) {
-                const uint32_t ci = __shfl_sync(FULL, mine, kk);
-                const int4 box = __ldg((const int4*)&A.boxes[ci]);   // l, r, t, b
-                if (box.w <= y0 || box.z >= y0 + 8) continue;         // misses this half of the tile
-                const NcrCmd* __restrict__ c = A.cmds + ci;
-                const uint2 head = __ldg((const uint2*)c);            // op, flags
-                const uint32_t op = head.x, flags = head.y;
-
-                // pixel-box membership (the reference's loop bounds) and 8x4-block culling
-                bool in[4];
-                FOR4 {
-                    const int px = xs[p & 1], py = ys[p >> 1];
-                    in[p] = valid[p] && px >= box.x && px < box.y && py >= box.z && py < box.w;
+        // Walk the tile's list in submission order.  32 entries at a time: each lane tests one command's box against
+        // this half-tile, the ballot is the set of commands to apply.
+        uint32_t k0 = 0, pending = 0, mine = 0;
+        auto next_cmd = [&]() -> int {   // warp-uniform: index of the next command touching this half, or -1
+            while (pending == 0) {
+                if (k0 >= lcount) return -1;
+                bool hit = false;
+                if (k0 + lane < lcount) {
+                    mine = __ldg(&A.fine_list[loff + k0 + lane]);
+                    const int4 box = __ldg((const int4*)&A.boxes[mine]);   // l, r, t, b
+                    hit = box.z < y0 + 8 && box.w > y0;
                 }
-
-                if (op == NCR_OP_SET_COLOR) {   // cpp:643-657
-                    const double c0 = __ldg(&c->p[0]), c1 = __ldg(&c->p[1]), c2 = __ldg(&c->p[2]), c3 = __ldg(&c->p[3]);
-                    FOR4 if (in[p]) {
-                        dr[p] = c0; dg[p] = c1; db[p] = c2;
-                        if (ALPHA) da[p] = c3;
-                        // 3-channel canvas, non-uniform colour: SetPixel's index+3 store (cpp:510) leaves `a` in the red
-                        // of pixel (0, j>=1), because column 0 is written first and the last column spills into it.
-                        else if ((flags & NCR_F_RGB_SPILL) && xs[p & 1] == 0 && ys[p >> 1] >= 1 && W > 1) dr[p] = c3;
-                    }
-                    continue;
-                }
-                if (op == NCR_OP_SET_PIXEL) {   // cpp:494-513
-                    const double c0 = __ldg(&c->p[0]), c1 = __ldg(&c->p[1]), c2 = __ldg(&c->p[2]), c3 = __ldg(&c->p[3]);
-                    FOR4 if (in[p]) {
-                        dr[p] = c0;
-                        if (!(flags & NCR_F_ONLY_RED)) {
-                            dg[p] = c1; db[p] = c2;
-                            if (ALPHA) da[p] = c3;
-                        }
-                    }
-                    continue;
-                }
-
-                if (op == NCR_OP_GRAD) {   // cpp:1299-1314
-                    const double i0 = __ldg(&c->inv[0]), i1 = __ldg(&c->inv[1]), i2 = __ldg(&c->inv[2]), i3 = __ldg(&c->inv[3]);
-                    const double i4 = __ldg(&c->inv[4]), i5 = __ldg(&c->inv[5]);
-                    const double cx = __ldg(&c->x), cy = __ldg(&c->y), cxw = __ldg(&c->xw), cyh = __ldg(&c->yh);
-                    const double hgt = __ldg(&c->sy);
-                    const double ax[2] = {MUL(i0, fx[0]), MUL(i0, fx[1])}, bx[2] = {MUL(i1, fx[0]), MUL(i1, fx[1])};
-                    const double ay[2] = {MUL(i2, fy[0]), MUL(i2, fy[1])}, by[2] = {MUL(i3, fy[0]), MUL(i3, fy[1])};
-                    FOR4 {
-                        if (!__any_sync(FULL, in[p])) continue;
-                        const double X = ADD(ADD(ax[p & 1], ay[p >> 1]), i4);   // cpp:451-452
-                        const double Y = ADD(ADD(bx[p & 1], by[p >> 1]), i5);
-                        if (in[p] && !(X < cx) && !(X > cxw) && !(Y < cy) && !(Y > cyh)) {
-                            const double t = DIV(SUB(Y, cy), hgt);   // cpp:1308; p[4..7] = bottom - top
-                            const double r = MUL(ADD(__ldg(&c->p[0]), MUL(__ldg(&c->p[4]), t)), __ldg(&c->ct[0]));
-                            const double g = MUL(ADD(__ldg(&c->p[1]), MUL(__ldg(&c->p[5]), t)), __ldg(&c->ct[1]));
-                            const double b = MUL(ADD(__ldg(&c->p[2]), MUL(__ldg(&c->p[6]), t)), __ldg(&c->ct[2]));
-                            const double a = MUL(ADD(__ldg(&c->p[3]), MUL(__ldg(&c->p[7]), t)), __ldg(&c->ct[3]));
-                            blend<ALPHA>(dr[p], dg[p], db[p], da[p], r, g, b, a);
-                            if (COUNT) ++n_applied;
-                        }
-                    }
-                    continue;
-                }
-
-                if (op == NCR_OP_RECT || op == NCR_OP_CIRCLE || op == NCR_OP_POLY || op == NCR_OP_FILL_COLOR ||
-                    op == NCR_OP_APPLY_PIXEL) {
-                    // constant colour: p[0..3] = colour * ct, p[4..6] = rgb*a, p[7] = 1-a, all formed on the host with the
-                    // same IEEE operations ApplyPixel performs per pixel (cpp:525-536).
-                    if (op != NCR_OP_FILL_COLOR && op != NCR_OP_APPLY_PIXEL) {
-                        const double i0 = __ldg(&c->inv[0]), i1 = __ldg(&c->inv[1]), i2 = __ldg(&c->inv[2]), i3 = __ldg(&c->inv[3]);
-                        const double i4 = __ldg(&c->inv[4]), i5 = __ldg(&c->inv[5]);
-                        const double cx = __ldg(&c->x), cy = __ldg(&c->y);
-                        const double ax[2] = {MUL(i0, fx[0]), MUL(i0, fx[1])}, bx[2] = {MUL(i1, fx[0]), MUL(i1, fx[1])};
-                        const double ay[2] = {MUL(i2, fy[0]), MUL(i2, fy[1])}, by[2] = {MUL(i3, fy[0]), MUL(i3, fy[1])};
-                        if (op == NCR_OP_RECT) {   // cpp:866-869
-                            const double cxw = __ldg(&c->xw), cyh = __ldg(&c->yh);
-                            FOR4 {
-                                if (!__any_sync(FULL, in[p])) continue;
-                                const double X = ADD(ADD(ax[p & 1], ay[p >> 1]), i4);
-                                const double Y = ADD(ADD(bx[p & 1], by[p >> 1]), i5);
-                                in[p] = in[p] && !(X < cx) && !(X > cxw) && !(Y < cy) && !(Y > cyh);
-                            }
-                        } else if (op == NCR_OP_CIRCLE) {   // cpp:939-943
-                            const double rad = __ldg(&c->sx);
-                            FOR4 {
-                                if (!__any_sync(FULL, in[p])) continue;
-                                const double X = ADD(ADD(ax[p & 1], ay[p >> 1]), i4);
-                                const double Y = ADD(ADD(bx[p & 1], by[p >> 1]), i5);
-                                const double ddx = SUB(X, cx), ddy = SUB(Y, cy);
-                                const double dist = __dsqrt_rn(ADD(MUL(ddx, ddx), MUL(ddy, ddy)));
-                                in[p] = in[p] && !(dist > rad);
-                            }
-                        } else {   // NCR_OP_POLY, cpp:913
-                            const double* pts = A.aux + __ldg(&c->aux_off);
-                            const uint32_t npts = __ldg(&c->aux_n);
-                            FOR4 {
-                                if (!__any_sync(FULL, in[p])) continue;
-                                const double X = ADD(ADD(ax[p & 1], ay[p >> 1]), i4);
-                                const double Y = ADD(ADD(bx[p & 1], by[p >> 1]), i5);
-                                in[p] = in[p] && point_in_poly(pts, npts, X, Y);
-                            }
-                        }
-                    }
-                    const double sa = __ldg(&c->p[3]);
-                    if (sa != 1.0) {
-                        const double q0 = __ldg(&c->p[4]), q1 = __ldg(&c->p[5]), q2 = __ldg(&c->p[6]), om = __ldg(&c->p[7]);
-                        FOR4 if (in[p]) {
-                            dr[p] = ADD(MUL(dr[p], om), q0);
-                            dg[p] = ADD(MUL(dg[p], om), q1);
-                            db[p] = ADD(MUL(db[p], om), q2);
-                            if (ALPHA) da[p] = sa;
-                            if (COUNT) ++n_applied;
-                        }
-                    } else {
-                        const double c0 = __ldg(&c->p[0]), c1 = __ldg(&c->p[1]), c2 = __ldg(&c->p[2]);
-                        FOR4 if (in[p]) {
-                            dr[p] = c0; dg[p] = c1; db[p] = c2;
-                            if (ALPHA) da[p] = sa;
-                            if (COUNT) ++n_applied;
-                        }
-                    }
-                    continue;
-                }
-
-                // ---- textured ops: DrawTexture (both paths), DrawSplittedTexture, perspective extension ----
-                const int2 twh = __ldg((const int2*)&c->tex_w);
-                const int tw = twh.x, th = twh.y;
-                const void* tex = (const void*)__ldg((const unsigned long long*)&c->tex);
-                const double cx = __ldg(&c->x), cy = __ldg(&c->y), cxw = __ldg(&c->xw), cyh = __ldg(&c->yh);
-                const double sx = __ldg(&c->sx), sy = __ldg(&c->sy);
-                double u[4], v[4];
-                if (op == NCR_OP_TEX_IDENT) {   // cpp:741-745: pixels i >= (i64)x with (f64)i < x + width; u = (i - x) * scaleX
-                    const double i0 = __ldg(&c->p[0]), j0 = __ldg(&c->p[1]);
-                    FOR4 {
-                        const double fi = fx[p & 1], fj = fy[p >> 1];
-                        in[p] = in[p] && fi >= i0 && fi < cxw && fj >= j0 && fj < cyh;
-                        u[p] = MUL(SUB(fi, cx), sx);
-                        v[p] = MUL(SUB(fj, cy), sy);
-                    }
-                } else if (op == NCR_OP_TEX_PERSP) {   // extension: row-major 3x3 inverse homography, then cpp:765-771
-                    const double h0 = __ldg(&c->inv[0]), h1 = __ldg(&c->inv[1]), h2 = __ldg(&c->inv[2]);
-                    const double h3 = __ldg(&c->inv[3]), h4 = __ldg(&c->inv[4]), h5 = __ldg(&c->inv[5]);
-                    const double h6 = __ldg(&c->p[0]), h7 = __ldg(&c->p[1]), h8 = __ldg(&c->p[2]);
-                    FOR4 {
-                        const double fi = fx[p & 1], fj = fy[p >> 1];
-                        const double hw = ADD(ADD(MUL(h6, fi), MUL(h7, fj)), h8);
-                        const double X = DIV(ADD(ADD(MUL(h0, fi), MUL(h1, fj)), h2), hw);
-                        const double Y = DIV(ADD(ADD(MUL(h3, fi), MUL(h4, fj)), h5), hw);
-                        in[p] = in[p] && hw > 0.0 && !(X < cx) && !(X > cxw) && !(Y < cy) && !(Y > cyh);
-                        u[p] = MUL(SUB(X, cx), sx);
-                        v[p] = MUL(SUB(Y, cy), sy);
-                    }
-                } else {   // NCR_OP_TEX / NCR_OP_TEX_SPLIT, cpp:763-771
-                    const double i0 = __ldg(&c->inv[0]), i1 = __ldg(&c->inv[1]), i2 = __ldg(&c->inv[2]), i3 = __ldg(&c->inv[3]);
-                    const double i4 = __ldg(&c->inv[4]), i5 = __ldg(&c->inv[5]);
-                    const double ax[2] = {MUL(i0, fx[0]), MUL(i0, fx[1])}, bx[2] = {MUL(i1, fx[0]), MUL(i1, fx[1])};
-                    const double ay[2] = {MUL(i2, fy[0]), MUL(i2, fy[1])}, by[2] = {MUL(i3, fy[0]), MUL(i3, fy[1])};
-                    FOR4 {
-                        u[p] = 0.0; v[p] = 0.0;
-                        if (!__any_sync(FULL, in[p])) continue;
-                        const double X = ADD(ADD(ax[p & 1], ay[p >> 1]), i4);
-                        const double Y = ADD(ADD(bx[p & 1], by[p >> 1]), i5);
-                        in[p] = in[p] && !(X < cx) && !(X > cxw) && !(Y < cy) && !(Y > cyh);
-                        u[p] = MUL(SUB(X, cx), sx);
-                        v[p] = MUL(SUB(Y, cy), sy);
-                    }
-                    if (op == NCR_OP_TEX_SPLIT) {
-                        // cpp:812-813: u = (uStart + (uEnd - uStart) * u / tex->width) * tex->width
-                        const double uS = __ldg(&c->p[0]), dU = __ldg(&c->p[1]), vS = __ldg(&c->p[2]), dV = __ldg(&c->p[3]);
-                        const double fw = __ldg(&c->p[4]), fh = __ldg(&c->p[5]);
-                        if (flags & NCR_F_SPLIT_POW2) {
-                            // width and height are powers of two: x / 2^k and x * 2^-k are the same correctly rounded value
-                            const double rw = __ldg(&c->p[6]), rh = __ldg(&c->p[7]);
-                            FOR4 {
-                                u[p] = MUL(ADD(uS, MUL(MUL(dU, u[p]), rw)), fw);
-                                v[p] = MUL(ADD(vS, MUL(MUL(dV, v[p]), rh)), fh);
-                            }
-                        } else {
-                            FOR4 if (__any_sync(FULL, in[p])) {
-                                u[p] = MUL(ADD(uS, DIV(MUL(dU, u[p]), fw)), fw);
-                                v[p] = MUL(ADD(vS, DIV(MUL(dV, v[p]), fh)), fh);
-                            }
-                        }
-                    }
-                }
-
-                const double ct3 = __ldg(&c->ct[3]);
-                const bool rgb_one = (flags & NCR_F_CT_RGB_ONE) != 0;   // r * 1.0 == r exactly: the multiply is skipped
-                double ct0 = 1.0, ct1 = 1.0, ct2 = 1.0;
-                if (!rgb_one) { ct0 = __ldg(&c->ct[0]); ct1 = __ldg(&c->ct[1]); ct2 = __ldg(&c->ct[2]); }
-
-                if (flags & NCR_F_TEX_FAST) {   // RGBA8 texels, nearest, < 2^31 texels
-                    const uint32_t* t32 = (const uint32_t*)tex;
-                    uint32_t tx[4];
-                    FOR4 {
-                        tx[p] = 0u;
-                        if (!__any_sync(FULL, in[p])) continue;
-                        clamp_uv(u[p], v[p], tw, th);                       // cpp:560-563
-                        int xi = __double2int_rz(u[p]), yi = __double2int_rz(v[p]);   // cpp:566 (i64) truncation
-                        xi = max(0, min(tw - 1, xi));                       // memory safety only
-                        yi = max(0, min(th - 1, yi));
-                        tx[p] = in[p] ? __ldg(t32 + (yi * tw + xi)) : 0u;
-                    }
-                    FOR4 if (in[p]) {
-                        double r = s_lut[((tx[p] & 255u) << 4) | l16];
-                        double g = s_lut[(((tx[p] >> 8) & 255u) << 4) | l16];
-                        double b = s_lut[(((tx[p] >> 16) & 255u) << 4) | l16];
-                        double a = s_lut[((tx[p] >> 24) << 4) | l16];
-                        if (!rgb_one) { r = MUL(r, ct0); g = MUL(g, ct1); b = MUL(b, ct2); }   // cpp:525-527
-                        a = MUL(a, ct3);                                                       // cpp:528
-                        blend<ALPHA>(dr[p], dg[p], db[p], da[p], r, g, b, a);
-                        if (COUNT) ++n_applied;
-                    }
-                } else {
-                    FOR4 if (in[p]) {
-                        double s[4];
-                        sample_slow(tex, flags, tw, th, s_lut, l16, u[p], v[p], s);
-                        blend<ALPHA>(dr[p], dg[p], db[p], da[p], MUL(s[0], ct0), MUL(s[1], ct1), MUL(s[2], ct2), MUL(s[3], ct3));
-                        if (COUNT) ++n_applied;
-                    }
-                }
+                pending = __ballot_sync(FULL, hit);
+                k0 += 32;
             }
+            const int kk = __ffs(pending) - 1;
+            pending &= pending - 1;
+            return (int)__shfl_sync(FULL, mine, kk);
+        };
+
+        int slot = 0;
+        int cur = next_cmd();
+        if (cur >= 0) {
+            if (lane < WORDS) ((uint4*)&s_cmd[warp][0])[lane] = __ldg((const uint4*)(A.cmds + cur) + lane);
+            __syncwarp();
+        }
+        while (cur >= 0) {
+            const int nxt = next_cmd();
+            uint4 pre = make_uint4(0, 0, 0, 0);
+            if (nxt >= 0 && lane < WORDS) pre = __ldg((const uint4*)(A.cmds + nxt) + lane);   // in flight during apply_cmd
+            apply_cmd<ALPHA, COUNT>(s_cmd[warp][slot], A, S, lut, lut_base, dr, dg, db, da, n_applied);
+            if (nxt >= 0 && lane < WORDS) ((uint4*)&s_cmd[warp][slot ^ 1])[lane] = pre;
+            __syncwarp();
+            slot ^= 1;
+            cur = nxt;
         }
 
         // tile write-back: canonical f64 canvas (only if something was drawn) and the fused (iu8)(v*255) image
         FOR4 if (valid[p]) {
-            const size_t pix = ((size_t)ys[p >> 1] * W + xs[p & 1]) * IPP;
+            const size_t pix = ((size_t)S.ys[p >> 1] * W + S.xs[p & 1]) * IPP;
             if (lcount != 0) {
                 double* q = A.fb + pix;
                 if (ALPHA) {
@@ -417,7 +541,7 @@ __global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, 4) ncr_composite(NcrFlu
                 if (ALPHA) {
                     const uint32_t o = (uint32_t)ncr_to_u8(dr[p]) | ((uint32_t)ncr_to_u8(dg[p]) << 8) |
                                        ((uint32_t)ncr_to_u8(db[p]) << 16) | ((uint32_t)ncr_to_u8(da[p]) << 24);
-                    ((uint32_t*)A.u8_out)[(size_t)ys[p >> 1] * W + xs[p & 1]] = o;
+                    ((uint32_t*)A.u8_out)[(size_t)S.ys[p >> 1] * W + S.xs[p & 1]] = o;
                 } else {
                     unsigned char* o = A.u8_out + pix;
                     o[0] = ncr_to_u8(dr[p]); o[1] = ncr_to_u8(dg[p]); o[2] = ncr_to_u8(db[p]);
