@@ -160,6 +160,33 @@ __device__ __forceinline__ double lut_byte(uint32_t base, uint32_t texel) {
 
 #define FOR4 _Pragma("unroll") for (int p = 0; p < 4; ++p)
 
+// Exact rejection of a command against a block of pixels [i0,i1] x [j0,j1] (inclusive), for the ops whose coverage is the
+// four inclusive bounds of cpp:765-768 on the inverse-mapped position.
+//
+// X(i,j) = fl(fl(fl(inv0*i) + fl(inv2*j)) + inv4) is monotone in i and in j separately (IEEE rounding is monotone), so its
+// maximum and minimum over the block are attained at block corners chosen by the signs of inv0 and inv2.  Evaluating the
+// SAME expression at those corners therefore bounds the value every pixel of the block will compute: if max X < x, every
+// pixel fails `invX < x -> continue`, and likewise for the other three bounds.  No tolerance is involved; a NaN bound
+// compares false and never rejects.
+__device__ __forceinline__ bool quad_misses_region(const NcrCmd* __restrict__ c, int i0, int i1, int j0, int j1) {
+    const uint32_t op = __ldg(&c->op);
+    if (op != NCR_OP_TEX && op != NCR_OP_TEX_SPLIT && op != NCR_OP_RECT && op != NCR_OP_GRAD) return false;
+    const double2 m01 = __ldg((const double2*)&c->inv[0]), m23 = __ldg((const double2*)&c->inv[2]);
+    const double2 m45 = __ldg((const double2*)&c->inv[4]);
+    const double2 lo = __ldg((const double2*)&c->x), hi = __ldg((const double2*)&c->xw);
+    const double fi0 = (double)i0, fi1 = (double)i1, fj0 = (double)j0, fj1 = (double)j1;
+    // X = (inv0*i + inv2*j) + inv4
+    const double xa_hi = MUL(m01.x, m01.x >= 0.0 ? fi1 : fi0), xa_lo = MUL(m01.x, m01.x >= 0.0 ? fi0 : fi1);
+    const double xb_hi = MUL(m23.x, m23.x >= 0.0 ? fj1 : fj0), xb_lo = MUL(m23.x, m23.x >= 0.0 ? fj0 : fj1);
+    const double x_max = ADD(ADD(xa_hi, xb_hi), m45.x), x_min = ADD(ADD(xa_lo, xb_lo), m45.x);
+    // Y = (inv1*i + inv3*j) + inv5
+    const double ya_hi = MUL(m01.y, m01.y >= 0.0 ? fi1 : fi0), ya_lo = MUL(m01.y, m01.y >= 0.0 ? fi0 : fi1);
+    const double yb_hi = MUL(m23.y, m23.y >= 0.0 ? fj1 : fj0), yb_lo = MUL(m23.y, m23.y >= 0.0 ? fj0 : fj1);
+    const double y_max = ADD(ADD(ya_hi, yb_hi), m45.y), y_min = ADD(ADD(ya_lo, yb_lo), m45.y);
+    return x_max < lo.x || x_min > hi.x || y_max < lo.y || y_min > hi.y;
+}
+
+
 // Per-lane pixel slots of the current half-tile.
 struct Slots {
     int xs[2], ys[2];        // pixel columns / rows owned by this lane
@@ -499,6 +526,8 @@ __global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, NCR_COMPOSITE_MIN_CTAS)
                     mine = __ldg(&A.fine_list[loff + k0 + lane]);
                     const int4 box = __ldg((const int4*)&A.boxes[mine]);   // l, r, t, b
                     hit = box.z < y0 + 8 && box.w > y0;
+                    if (hit) hit = !quad_misses_region(A.cmds + mine, max(x0, box.x), min(x0 + NCR_TILE, box.y) - 1,
+                                                       max(y0, box.z), min(y0 + 8, box.w) - 1);
                 }
                 pending = __ballot_sync(FULL, hit);
                 k0 += 32;

@@ -21,50 +21,71 @@ __device__ __forceinline__ bool box_hits(const NcrBox& bx, int x0, int y0, int x
     return bx.l < bx.r && bx.t < bx.b && bx.l < x1 && bx.r > x0 && bx.t < y1 && bx.b > y0;
 }
 
+// One CTA per 128x128-px bin.  The command range is cut into 8 contiguous segments, one per warp; each warp counts its
+// hits (ballot + popc, four independent box loads in flight per lane), one block-level prefix gives every warp its write
+// position, and the warps re-scan their segments writing command indices in submission order.  No barrier inside the
+// loops.  Lists of different bins are carved out of one array with a single atomicAdd per bin.
 __global__ void __launch_bounds__(256) ncr_bin_coarse(NcrFlushArgs A) {
     const int bin = blockIdx.x;
+    const int n_bins = A.d.bins_x * A.d.bins_y;
     const int bx = bin % A.d.bins_x, by = bin / A.d.bins_x;
     const int edge = NCR_TILE * NCR_COARSE;
     const int x0 = bx * edge, y0 = by * edge, x1 = x0 + edge, y1 = y0 + edge;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __shared__ uint32_t s_warp[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ uint32_t s_count[8];
     __shared__ uint32_t s_base;
 
+    const uint32_t n = A.n_cmds;
+    const uint32_t seg = ((n + 7) / 8 + 31) & ~31u;   // per-warp segment, multiple of 32
+    const uint32_t beg = min(n, warp * seg), end = min(n, beg + seg);
+
     uint32_t count = 0;
-    for (uint32_t base = 0; base < A.n_cmds; base += 256) {
-        uint32_t idx = base + tid;
-        bool hit = idx < A.n_cmds && box_hits(A.boxes[idx], x0, y0, x1, y1);
-        count += __syncthreads_count(hit);
+    for (uint32_t base = beg; base < end; base += 128) {
+        bool hit[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t idx = base + k * 32 + lane;
+            const NcrBox b = A.boxes[min(idx, n - 1)];   // unconditional (clamped) load: the four loads overlap
+            hit[k] = box_hits(b, x0, y0, x1, y1) && idx < end;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) count += __popc(__ballot_sync(0xffffffffu, hit[k]));
     }
-    if (tid == 0) {
-        uint32_t off = atomicAdd(&A.cursors[0], count);
-        if (off + count > A.coarse_cap) { count = 0; atomicExch(&A.cursors[4], 1u); }
+    if (lane == 0) s_count[warp] = count;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+        for (int w = 0; w < 8; ++w) total += s_count[w];
+        uint32_t off = atomicAdd(&A.cursors[0], total);
+        if (off + total > A.coarse_cap) { total = 0; atomicExch(&A.cursors[4], 1u); }
         s_base = off;
         A.coarse_off[bin] = off;
-        A.coarse_off[A.d.bins_x * A.d.bins_y + bin] = count;
+        A.coarse_off[n_bins + bin] = total;
+        if (total == 0) s_base = 0xffffffffu;
     }
     __syncthreads();
-    if (A.coarse_off[A.d.bins_x * A.d.bins_y + bin] == 0) return;
-    uint32_t running = s_base;
-    for (uint32_t base = 0; base < A.n_cmds; base += 256) {
-        uint32_t idx = base + tid;
-        bool hit = idx < A.n_cmds && box_hits(A.boxes[idx], x0, y0, x1, y1);
-        uint32_t m = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0) s_warp[warp] = __popc(m);
-        __syncthreads();
-        uint32_t before = 0, total = 0;
+    if (s_base == 0xffffffffu) return;
+    uint32_t pos = s_base;
+    for (int w = 0; w < warp; ++w) pos += s_count[w];
+    for (uint32_t base = beg; base < end; base += 128) {
+        bool hit[4];
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            uint32_t c = s_warp[w];
-            before += (w < warp) ? c : 0;
-            total += c;
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t idx = base + k * 32 + lane;
+            const NcrBox b = A.boxes[min(idx, n - 1)];   // unconditional (clamped) load: the four loads overlap
+            hit[k] = box_hits(b, x0, y0, x1, y1) && idx < end;
         }
-        if (hit) A.coarse_list[running + before + __popc(m & ((1u << lane) - 1))] = idx;
-        running += total;
-        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t m = __ballot_sync(0xffffffffu, hit[k]);
+            if (hit[k]) A.coarse_list[pos + __popc(m & ((1u << lane) - 1))] = base + k * 32 + lane;
+            pos += __popc(m);
+        }
     }
 }
 
+// One warp per 16x16-px tile: the tile's bin list is filtered by the tile's pixel rectangle, 128 candidates per step
+// (four independent index -> box load chains per lane), and compacted in order with ballot + popc.
 __global__ void __launch_bounds__(256) ncr_bin_fine(NcrFlushArgs A) {
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -77,10 +98,22 @@ __global__ void __launch_bounds__(256) ncr_bin_fine(NcrFlushArgs A) {
     const uint32_t ccount = A.coarse_off[A.d.bins_x * A.d.bins_y + bin];
 
     uint32_t count = 0;
-    for (uint32_t k = 0; k < ccount; k += 32) {
-        bool hit = false;
-        if (k + lane < ccount) hit = box_hits(A.boxes[A.coarse_list[cbase + k + lane]], x0, y0, x1, y1);
-        count += __popc(__ballot_sync(0xffffffffu, hit));
+    if (ccount == 0) {
+        if (lane == 0) { A.fine_off[tile] = 0; A.fine_off[n_tiles + tile] = 0; }
+        return;
+    }
+    for (uint32_t k = 0; k < ccount; k += 128) {
+        uint32_t idx[4];
+        bool hit[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) idx[u] = A.coarse_list[cbase + min(k + u * 32 + lane, ccount - 1)];   // clamped, unconditional
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const NcrBox b = A.boxes[idx[u]];
+            hit[u] = box_hits(b, x0, y0, x1, y1) && (k + u * 32 + lane < ccount);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) count += __popc(__ballot_sync(0xffffffffu, hit[u]));
     }
     uint32_t off = 0;
     if (lane == 0) {
@@ -92,16 +125,22 @@ __global__ void __launch_bounds__(256) ncr_bin_fine(NcrFlushArgs A) {
     off = __shfl_sync(0xffffffffu, off, 0);
     count = __shfl_sync(0xffffffffu, count, 0);
     if (count == 0) return;
-    for (uint32_t k = 0; k < ccount; k += 32) {
-        bool hit = false;
-        uint32_t idx = 0;
-        if (k + lane < ccount) {
-            idx = A.coarse_list[cbase + k + lane];
-            hit = box_hits(A.boxes[idx], x0, y0, x1, y1);
+    for (uint32_t k = 0; k < ccount; k += 128) {
+        uint32_t idx[4];
+        bool hit[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) idx[u] = A.coarse_list[cbase + min(k + u * 32 + lane, ccount - 1)];   // clamped, unconditional
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const NcrBox b = A.boxes[idx[u]];
+            hit[u] = box_hits(b, x0, y0, x1, y1) && (k + u * 32 + lane < ccount);
         }
-        uint32_t m = __ballot_sync(0xffffffffu, hit);
-        if (hit) A.fine_list[off + __popc(m & ((1u << lane) - 1))] = idx;
-        off += __popc(m);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t m = __ballot_sync(0xffffffffu, hit[u]);
+            if (hit[u]) A.fine_list[off + __popc(m & ((1u << lane) - 1))] = idx[u];
+            off += __popc(m);
+        }
     }
 }
 
