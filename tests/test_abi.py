@@ -100,3 +100,28 @@ def test_no_gpu_fails_loudly_not_silently():
     assert res.returncode == 0, res.stderr
     assert "PTR None |" in res.stdout
     assert "no usable CUDA device" in res.stdout
+
+
+REF_PYB = "/root/reference/src/libNativeCPURendererPybind.py"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PYB), reason="reference checkout not present (GPU box)")
+def test_reference_binding_imports_against_the_product_unchanged(tmp_path):
+    """The reference's own ctypes binding (pyb:9 loads ./libNativeCPURenderer.so with RTLD_NOW) must import against the
+    product library from a directory that holds nothing but that file, and reach host-only entry points through it."""
+    from libnativecpurenderer_b200.binding import default_library_path
+
+    os.symlink(default_library_path(), tmp_path / "libNativeCPURenderer.so")
+    code = (
+        "import sys; sys.path.insert(0, '/root/reference/src')\n"
+        "import libNativeCPURendererPybind as CPURenderer\n"
+        "print('VERSION', CPURenderer.get_version())\n"
+        "clip = CPURenderer.AudioClip.slient(8000, 2, 50)\n"
+        "print('WAV', len(clip.save_as_wav()), clip.duration)\n"
+        "missing = [n for n in %r if not hasattr(CPURenderer.lib, n)]\n"
+        "print('MISSING', missing)\n" % (REFERENCE_EXPORTS,)
+    )
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=tmp_path, timeout=300)
+    assert res.returncode == 0, res.stderr
+    assert "VERSION 1" in res.stdout and "MISSING []" in res.stdout
+    assert "WAV 244 0.00625" in res.stdout
