@@ -204,6 +204,10 @@ __device__ __forceinline__ void shade_rgba8(const NcrCmd& c, uint32_t lut_base, 
     if (!RGB_ONE) { ct0 = c.ct[0]; ct1 = c.ct[1]; ct2 = c.ct[2]; }
     bool opaque[4];
     FOR4 {
+        opaque[p] = false;
+#ifdef NCR_SLOT_SKIP
+        if (!__any_sync(FULL, in[p])) continue;   // no lane of this 8x4 block is covered
+#endif
         const uint32_t t = tx[p];
         double r = lut_byte<0>(lut_base, t), g = lut_byte<1>(lut_base, t), b = lut_byte<2>(lut_base, t);
         double a = lut_byte<3>(lut_base, t);
@@ -294,6 +298,11 @@ __device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A
     bool in[4];
     FOR4 in[p] = inx[p & 1] && iny[p >> 1];
 
+    if (flags & NCR_F_FAST_AFFINE) {   // DrawTexture / DrawSplittedTexture on RGBA8, nearest: the hot case, tested first
+        tex_fast<ALPHA, COUNT>(c, op, flags, S, lut, lut_base, in, dr, dg, db, da, n_applied);
+        return;
+    }
+
     if (op == NCR_OP_SET_COLOR) {   // cpp:643-657
         FOR4 if (in[p]) {
             dr[p] = c.p[0]; dg[p] = c.p[1]; db[p] = c.p[2];
@@ -312,11 +321,6 @@ __device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A
                 if (ALPHA) da[p] = c.p[3];
             }
         }
-        return;
-    }
-
-    if ((op == NCR_OP_TEX || op == NCR_OP_TEX_SPLIT) && (flags & NCR_F_TEX_FAST)) {
-        tex_fast<ALPHA, COUNT>(c, op, flags, S, lut, lut_base, in, dr, dg, db, da, n_applied);
         return;
     }
 

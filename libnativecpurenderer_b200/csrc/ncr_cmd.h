@@ -37,6 +37,7 @@ enum : uint32_t {
     NCR_F_CT_RGB_ONE = 1u << 6,   // ct[0..2] are all exactly 1.0: v * 1.0 == v, the multiplies are skipped
     NCR_F_SPLIT_POW2 = 1u << 7,   // TEX_SPLIT: texture width and height are powers of two; p[6], p[7] = 1/w, 1/h (exact)
     NCR_F_TEX_FAST = 1u << 8,     // RGBA8 texels, nearest sampling, fewer than 2^31 texels: inlined sampler
+    NCR_F_FAST_AFFINE = 1u << 9,  // NCR_OP_TEX / NCR_OP_TEX_SPLIT with NCR_F_TEX_FAST: the composite's first-tested path
 };
 
 struct alignas(16) NcrCmd {

@@ -321,3 +321,52 @@ def stream_random(ctx, textures, seed: int, n: int = 60, use_apply_pixel: bool =
             ctx.apply_pixel(rng.randrange(-2, W + 2), rng.randrange(-2, H + 2), *colour())
     for _ in range(depth):
         ctx.restore_state()
+
+
+# --------------------------------------------------------------------------------------------- extensions (parity unpinned)
+def stream_extensions(ctx, textures, seed: int, n: int = 60) -> None:
+    """The entry points BASELINE's configs name that the reference does not have (include/ncr_b200.h §2): clip rects,
+    bilinear sampling, N-gon fill, perspective quads — mixed with reference-ABI draws.  Product vs C restatement only."""
+    W, H = ctx.width, ctx.height
+    rng = random.Random(seed)
+    u = rng.uniform
+    ctx.set_color(.15, .15, .2, 1)
+    for k in range(n):
+        ctx.save_state()
+        ctx.translate(u(0, W), u(0, H))
+        ctx.rotate(u(0, TWO_PI))
+        s = u(.3, 1.4)
+        ctx.scale(s, s)
+        ctx.apply_color_transform(1, u(.6, 1), 1, rng.choice([1.0, u(.2, 1)]))
+        op = rng.random()
+        if op < .15:
+            ctx.set_clip_rect(int(u(0, W * .6)), int(u(0, H * .6)), int(u(8, W * .7)), int(u(8, H * .7)))
+        elif op < .25:
+            ctx.clear_clip_rect()
+        elif op < .35:
+            ctx.set_sampling(rng.choice([0, 1]))
+        elif op < .55:
+            pts = [(u(-60, 60), u(-60, 60)) for _ in range(rng.choice([3, 5, 7]))]
+            ctx.fill_polygon(pts, u(0, 1), u(0, 1), u(0, 1), rng.choice([1.0, u(.2, 1)]))
+        elif op < .70:
+            tex = rng.choice(textures)
+            # inverse homography: a mild projective warp around the translate point
+            tx_, ty_ = u(0, W), u(0, H)
+            c_, s_ = math.cos(u(0, TWO_PI)), math.sin(u(0, TWO_PI))
+            k_ = u(.5, 2)
+            hinv = (c_ * k_, s_ * k_, -(c_ * k_ * tx_ + s_ * k_ * ty_), -s_ * k_, c_ * k_, (s_ * k_ * tx_ - c_ * k_ * ty_),
+                    u(-1e-3, 1e-3), u(-1e-3, 1e-3), 1.0)
+            ctx.draw_texture_perspective(tex, hinv, -40, -30, 80, 60)
+        elif op < .85:
+            tex = rng.choice(textures)
+            ctx.draw_texture(tex, -tex.width / 2, -tex.height / 2, tex.width, tex.height)
+        elif op < .92:
+            ctx.draw_line(-50, u(-20, 20), 50, u(-20, 20), u(1, 9), u(0, 1), u(0, 1), u(0, 1), u(.3, 1))
+        elif op < .96:
+            ctx.fill_color(u(0, 1), u(0, 1), u(0, 1), u(.05, .3))
+        else:
+            tex = rng.choice(textures)
+            ctx.draw_splitted_texture(tex, -30, -30, 60, 60, 0.1, 0.9, 0.2, 0.8)
+        ctx.restore_state()
+    ctx.clear_clip_rect()
+    ctx.set_sampling(0)

@@ -37,6 +37,10 @@ typedef struct Canvas {
     State st;
     State* stack;
     i64 depth, cap;
+    /* extensions (no reference implementation; PARITY UNPINNED): clip rect and sampling mode */
+    int clip_on;
+    i64 cl, cr, ct, cb;
+    int bilinear;
 } Canvas;
 
 typedef struct Image {
@@ -104,6 +108,17 @@ static Box border(const Canvas* c, f64 x, f64 y, f64 w, f64 h) {
     return o;
 }
 
+/* extension: every draw's pixel box is intersected with the clip rect */
+static Box clipped(const Canvas* c, Box b) {
+    if (c->clip_on) {
+        if (b.l < c->cl) b.l = c->cl;
+        if (b.r > c->cr) b.r = c->cr;
+        if (b.t < c->ct) b.t = c->ct;
+        if (b.b > c->cb) b.b = c->cb;
+    }
+    return b;
+}
+
 /* cpp:515-549 */
 static void blend(Canvas* c, i64 i, i64 j, f64 r, f64 g, f64 b, f64 a) {
     if (i < 0 || i >= c->w || j < 0 || j >= c->h) return;
@@ -130,6 +145,26 @@ static void texel(const Image* t, f64 u, f64 v, f64* out) {
     out[3] = t->ipp == 4 ? s[3] : 1.0;
 }
 
+/* extension: the four-tap formula the reference keeps commented out at cpp:575-620 (same clamp as cpp:560-563) */
+static void texel_bilinear(const Image* t, f64 u, f64 v, f64* out) {
+    if (u < 0) u = 0;
+    if (u >= t->w - 1) u = t->w - 2;
+    if (v < 0) v = 0;
+    if (v >= t->h - 1) v = t->h - 2;
+    i64 xi = clampi(trunc64(u), 0, t->w - 1), yi = clampi(trunc64(v), 0, t->h - 1);
+    i64 dx = xi + 1 < t->w ? 1 : 0, dy = yi + 1 < t->h ? 1 : 0;
+    f64 fu = u - (f64)xi, fv = v - (f64)yi, mu = 1.0 - fu, mv = 1.0 - fv;
+    const f64* s0 = t->px + (yi * t->w + xi) * t->ipp;
+    const f64* s1 = t->px + (yi * t->w + xi + dx) * t->ipp;
+    const f64* s2 = t->px + ((yi + dy) * t->w + xi) * t->ipp;
+    const f64* s3 = t->px + ((yi + dy) * t->w + xi + dx) * t->ipp;
+    for (int k = 0; k < 4; ++k) {
+        f64 c0 = (k < t->ipp) ? s0[k] : 1.0, c1 = (k < t->ipp) ? s1[k] : 1.0;
+        f64 c2 = (k < t->ipp) ? s2[k] : 1.0, c3 = (k < t->ipp) ? s3[k] : 1.0;
+        out[k] = c0 * mu * mv + c1 * fu * mv + c2 * mu * fv + c3 * fu * fv;
+    }
+}
+
 /* cpp:822-845 */
 static bool inside_poly(const f64* p, int n, f64 x, f64 y) {
     bool in = false;
@@ -141,7 +176,7 @@ static bool inside_poly(const f64* p, int n, f64 x, f64 y) {
 }
 
 /* ---------------------------------------------------------------- generic rasteriser */
-enum { K_RECT, K_TEX, K_SPLIT, K_GRAD, K_CIRCLE, K_POLY };
+enum { K_RECT, K_TEX, K_SPLIT, K_GRAD, K_CIRCLE, K_POLY, K_PERSP };
 
 typedef struct {
     int kind;
@@ -154,13 +189,23 @@ typedef struct {
     f64 us, du, vs, dv;
     const f64* pts;
     int npts;
+    f64 hom[3];   /* K_PERSP: third row of the inverse homography (inv[] holds the first two rows, row-major) */
 } Shader;
 
 static void raster(Canvas* c, Box bx, const Shader* s) {
+    bx = clipped(c, bx);
     for (i64 j = bx.t; j < bx.b; ++j) {
         for (i64 i = bx.l; i < bx.r; ++i) {
             f64 X, Y, rgba[4];
-            map_point(s->inv, (f64)i, (f64)j, &X, &Y);
+            if (s->kind == K_PERSP) {   /* extension: X = (h0*i + h1*j + h2) / (h6*i + h7*j + h8), likewise Y */
+                f64 fi = (f64)i, fj = (f64)j;
+                f64 hw = s->hom[0] * fi + s->hom[1] * fj + s->hom[2];
+                X = (s->inv[0] * fi + s->inv[1] * fj + s->inv[2]) / hw;
+                Y = (s->inv[3] * fi + s->inv[4] * fj + s->inv[5]) / hw;
+                if (!(hw > 0.0)) continue;
+            } else {
+                map_point(s->inv, (f64)i, (f64)j, &X, &Y);
+            }
             if (s->kind == K_CIRCLE) {   /* cpp:939-943 */
                 f64 dx = X - s->x, dy = Y - s->y;
                 if (sqrt(dx * dx + dy * dy) > s->radius) continue;
@@ -181,7 +226,8 @@ static void raster(Canvas* c, Box bx, const Shader* s) {
                         u = (s->us + s->du * u / s->tex->w) * s->tex->w;
                         v = (s->vs + s->dv * v / s->tex->h) * s->tex->h;
                     }
-                    texel(s->tex, u, v, rgba);
+                    if (c->bilinear) texel_bilinear(s->tex, u, v, rgba);
+                    else texel(s->tex, u, v, rgba);
                 }
             }
             blend(c, i, j, rgba[0], rgba[1], rgba[2], rgba[3]);
@@ -287,8 +333,10 @@ void GetColor(Canvas* c, f64 x, f64 y, f64* r, f64* g, f64* b, f64* a) {   /* cp
     if (c->ipp == 4) *a = s[3];
 }
 void FillColor(Canvas* c, f64 r, f64 g, f64 b, f64 a) {   /* cpp:682-691 */
-    for (i64 j = 0; j < c->h; ++j)
-        for (i64 i = 0; i < c->w; ++i) blend(c, i, j, r, g, b, a);
+    Box all = {0, c->w, 0, c->h};
+    all = clipped(c, all);
+    for (i64 j = all.t; j < all.b; ++j)
+        for (i64 i = all.l; i < all.r; ++i) blend(c, i, j, r, g, b, a);
 }
 
 /* ---------------------------------------------------------------- C ABI: primitives */
@@ -317,10 +365,13 @@ void DrawTexture(Canvas* c, Image* tex, f64 x, f64 y, f64 w, f64 h) {   /* cpp:7
         /* cpp:741-750: i from (i64)x while i < x + w; the matrix is ignored; blend() clips */
         i64 i0 = trunc64(x), j0 = trunc64(y);
         f64 xw = x + w, yh = y + h;
-        for (i64 j = j0 < 0 ? 0 : j0; j < c->h && (f64)j < yh; ++j)
-            for (i64 i = i0 < 0 ? 0 : i0; i < c->w && (f64)i < xw; ++i) {
+        Box all = {0, c->w, 0, c->h};
+        all = clipped(c, all);
+        for (i64 j = j0 < all.t ? all.t : j0; j < all.b && (f64)j < yh; ++j)
+            for (i64 i = i0 < all.l ? all.l : i0; i < all.r && (f64)i < xw; ++i) {
                 f64 rgba[4];
-                texel(t, ((f64)i - x) * sx, ((f64)j - y) * sy, rgba);
+                if (c->bilinear) texel_bilinear(t, ((f64)i - x) * sx, ((f64)j - y) * sy, rgba);
+                else texel(t, ((f64)i - x) * sx, ((f64)j - y) * sy, rgba);
                 blend(c, i, j, rgba[0], rgba[1], rgba[2], rgba[3]);
             }
         release_operand(t);
@@ -483,3 +534,41 @@ Image* CreateMilthmHitEffectTexture(Image* mask, f64 seed, f64 t, f64 r, f64 g, 
 }
 
 long GetVersion(void) { return 1; }
+
+/* ---------------------------------------------------------------- extensions (include/ncr_b200.h section 2; PARITY UNPINNED:
+ * the reference implements none of these, so this is only this repository's own second implementation of the same spec) */
+void NcrSetClipRect(Canvas* c, long x, long y, long w, long h) {
+    c->clip_on = 1;
+    c->cl = x < 0 ? 0 : x;
+    c->ct = y < 0 ? 0 : y;
+    c->cr = x + w > c->w ? c->w : x + w;
+    c->cb = y + h > c->h ? c->h : y + h;
+}
+void NcrClearClipRect(Canvas* c) { c->clip_on = 0; }
+void NcrSetSampling(Canvas* c, int mode) { c->bilinear = mode == 1; }
+
+void NcrFillPolygon(Canvas* c, const f64* xy, long n, f64 r, f64 g, f64 b, f64 a) {   /* cpp:822-845 rule for N points */
+    if (n <= 0) return;
+    Shader s;
+    memset(&s, 0, sizeof s);
+    s.kind = K_POLY; s.pts = xy; s.npts = (int)n;
+    invert(c->st.m, s.inv);
+    s.col[0] = r; s.col[1] = g; s.col[2] = b; s.col[3] = a;
+    Box all = {0, c->w, 0, c->h};
+    raster(c, all, &s);
+}
+
+void NcrDrawTexturePerspective(Canvas* c, Image* tex, const f64* hinv, f64 x, f64 y, f64 w, f64 h) {
+    if (w == 0 || h == 0) return;
+    Image tmp;
+    const Image* t = operand(c, tex, &tmp);
+    Shader s;
+    memset(&s, 0, sizeof s);
+    s.kind = K_PERSP; s.tex = t;
+    for (int k = 0; k < 6; ++k) s.inv[k] = hinv[k];
+    s.hom[0] = hinv[6]; s.hom[1] = hinv[7]; s.hom[2] = hinv[8];
+    s.x = x; s.y = y; s.xw = x + w; s.yh = y + h; s.sx = t->w / w; s.sy = t->h / h;
+    Box all = {0, c->w, 0, c->h};
+    raster(c, all, &s);
+    release_operand(t);
+}

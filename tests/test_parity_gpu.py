@@ -247,3 +247,33 @@ def test_c3_full_size_properties(gpu):
         st = ctx.stats()
         assert st.n_cmds > 40000 and st.fine_entries > st.n_cmds
     assert hashes[0] == hashes[1]
+
+
+# ---- extensions: no reference implementation exists, so this is product vs this repo's own C restatement only ----------
+@pytest.mark.parametrize("seed", range(6))
+def test_extensions_match_port_parity_unpinned(seed, gpu, port, image_rgba):
+    """Clip rect, bilinear sampling, N-gon fill and perspective quads (include/ncr_b200.h §2).  PARITY UNPINNED: the
+    reference has none of these; both sides implement the specs of SURVEY.md §8c.  RGB and RGBA canvases, u8 and f64 textures."""
+    w, h, alpha = [(160, 90, True), (97, 61, False), (256, 144, True)][seed % 3]
+    got = []
+    for R in (gpu, port):
+        ctx = R.RenderContext(w, h, alpha)
+        tex = cases.tiny_textures(R, image_rgba)
+        tex.append(R.Texture(7, 6, True, np.random.RandomState(5).rand(6, 7, 4).tobytes(), is_uint8=False))
+        tex.append(R.Texture.from_numpy(np.random.RandomState(8).randint(0, 256, (12, 10, 3)).astype(np.uint8)))
+        streams.stream_extensions(ctx, tex, seed, n=80)
+        got.append(cases.digest(ctx))
+    assert got[0] == got[1]
+
+
+def test_clip_rect_limits_every_draw_kind(gpu):
+    ctx = gpu.RenderContext(64, 48, True)
+    ctx.set_color(0, 0, 0, 0)
+    ctx.set_clip_rect(10, 8, 20, 16)
+    ctx.fill_color(1, 1, 1, 1)
+    ctx.draw_rect(0, 0, 64, 48, 1, 0, 0, 1)
+    ctx.draw_line(0, 0, 64, 48, 9, 0, 1, 0, 1)
+    ctx.clear_clip_rect()
+    img = ctx.get_buffer_np().reshape(48, 64, 4)
+    touched = img[..., 3] != 0
+    assert touched[8:24, 10:30].all() and touched.sum() == 20 * 16
