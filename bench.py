@@ -45,6 +45,8 @@ WORKLOADS = {
                              "2% DrawLine; rotated/scaled, per-draw alpha), nearest sampling, seed 2"),
     "c3": (3840, 2160, True, "BASELINE config 3 (affine variant, SURVEY C3): 3840x2160 RGBA, 50,000 atlas sprites via "
                              "DrawSplittedTexture from a 2048^2 8x8-cell atlas, seed 3"),
+    "bg": (1920, 1080, True, "low-overdraw end of the path: 1920x1080 RGBA, SetColor + full-screen DrawTexture (identity path) + FillColor "
+                            "dim, u8 readback (3 commands per tile; the HBM-leaning regime)"),
     "c4": (1920, 1080, False, "BASELINE config 4 frame (SURVEY C4): 1920x1080 RGB milrenderer-shaped chart frame, ~1,500 notes, "
                               "12 lines, 100 hit effects, u8 readback"),
 }
@@ -68,6 +70,13 @@ def build_workload(name: str, n_draws: int | None = None):
         tex_np = [streams.make_atlas()]
         full = 50000
         streams.stream_c3(rec, trace.TexSlot(0, 2048, 2048), n=n_draws or full)
+    elif name == "bg":
+        tex_np = [np.ascontiguousarray(np.resize(streams.make_noise_texture(256, 7), (h, w, 4)))]
+        full = 2
+        slot = trace.TexSlot(0, w, h)
+        rec.set_color(0, 0, 0, 1)
+        rec.draw_texture(slot, 0, 0, w, h)
+        rec.fill_color(0, 0, 0, .6)
     elif name == "c4":
         chart = streams.make_chart_textures()
         bg = np.ascontiguousarray(np.resize(streams.make_noise_texture(256, 7), (h, w, 4)))
@@ -190,7 +199,7 @@ def run_reference(args) -> None:
     threads = min(host_threads(), 64)
     _, _, _, _, _, _, full = build_workload(args.workload, 8)
     # one full C2 frame is ~16 s of one core; size the per-step sample so K+W steps end within ~2.5 minutes
-    per_frame_s = {"c1": 1.1, "c2": 16.0, "c3": 60.0, "c4": 3.0}[args.workload]
+    per_frame_s = {"c1": 1.1, "c2": 16.0, "c3": 60.0, "c4": 3.0, "bg": 0.1}[args.workload]
     budget = 150.0 / max(1, args.steps + args.warmup)
     sample = int(max(min(full, 200), min(full, full * budget / per_frame_s)))
     fps, kind, text, step_s = cpu_arm(args.workload, threads, sample, args.steps, args.warmup)
@@ -293,7 +302,7 @@ def run_product(args) -> None:
 
     # ---- e2e: host buffers in, host frame out, through the reference C ABI --------------------------------
     rp = trace.Replayer(os.path.join(ROOT, "oracle", "libncr_replay.so"), R.path)   # the replayer is only a C caller
-    T = args.e2e_threads or min(4, host_threads())
+    T = args.e2e_threads or min(8, max(1, host_threads() // max(1, world)))
     e2e_frames_per_thread = max(2, min(K, args.e2e_frames))
     barrier()
     e2e_s = rp.run_threads(T, w, h, alpha, arr, tex, repeats=e2e_frames_per_thread, warm_repeats=3)
@@ -315,6 +324,10 @@ def run_product(args) -> None:
     achieved = algo / (comp_ms * 1e-3) / 1e9
     # f64 pipe view: ~26 f64 flops per blended pixel-op
     blended_per_s = blended * value / world
+    # FP64-pipe view: the reference's expression trees cost >= 26 f64 operations per blended pixel-op
+    #  and may not be fused; the peak is the measured rate of non-fused DMUL/DADD on this GPU.
+    f64_peak = R.lib.NcrMeasureF64Rate()
+    f64_achieved = blended * 26.0 / (comp_ms * 1e-3)
 
     line = {
         "metric": metric_name(args.workload), "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -336,6 +349,10 @@ def run_product(args) -> None:
                      "note": "high-overdraw streams are bound by the FP64 pipe, not HBM (DESIGN.md); see blended_gpixel_per_s"},
         "kernel_ms": {"step": float(per[:, 0].mean()), "ncr_bin_coarse": float(per[:, 1].mean()),
                       "ncr_bin_fine": float(per[:, 2].mean()), "ncr_composite": comp_ms},
+        "roofline_fp64": {"bound": "fp64 pipe (non-fused mul/add)", "kernel": "ncr_composite", "achieved": f64_achieved / 1e12,
+                          "peak": f64_peak / 1e12, "unit": "T f64 instr/s", "frac": (f64_achieved / f64_peak) if f64_peak else None,
+                          "algorithmic_f64_ops_per_blended_pixel_op": 26,
+                          "peak_source": "measured in this run: NcrMeasureF64Rate (8 independent DMUL->DADD chains per thread)"},
         "blended_gpixel_per_s": sum_over_ranks(blended_per_s) / 1e9 if dist else blended_per_s / 1e9,
         "gpixel_per_s": value * w * h / 1e9,
         "device": R.lib.NcrDeviceName().decode(),
@@ -344,7 +361,7 @@ def run_product(args) -> None:
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = min(host_threads(), 64)
-        sample = {"c1": 1000, "c2": 20000, "c3": 12000, "c4": 1500}[args.workload]
+        sample = {"c1": 1000, "c2": 20000, "c3": 12000, "c4": 1500, "bg": 2}[args.workload]
         fps, kind, text, _ = cpu_arm(args.workload, threads, sample, 1, 0)
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind, "sample": text}
     elif rank == 0:

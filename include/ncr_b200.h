@@ -136,6 +136,7 @@ int NcrRerunLastFlush(RenderContext* ctx, int iters, int flush_l2, float* ms_out
 void NcrGetStats(RenderContext* ctx, NcrStats* out);
 void NcrSetStatsMode(RenderContext* ctx, int mode); /* bit 0: count blended pixels, bit 1: per-kernel events */
 unsigned long long NcrKernelLaunchCount(void);      /* kernels launched by this library since load (all contexts) */
+double NcrMeasureF64Rate(void);                     /* measured rate of non-fused f64 mul/add instructions per second (roofline aid) */
 
 /* Extensions without a reference implementation (parity unpinned). */
 void NcrSetClipRect(RenderContext* ctx, long x, long y, long width, long height); /* intersects every draw's pixel box */

@@ -94,6 +94,7 @@ _EXT_ABI = {
     "NcrFillPolygon": (None, (_P, _P, c_long) + (_D,) * 4),
     "NcrDrawTexturePerspective": (None, (_P, _P, _P) + (_D,) * 4),
     "NcrKernelLaunchCount": (c_ulonglong, ()),
+    "NcrMeasureF64Rate": (c_double, ()),
 }
 
 

@@ -1100,6 +1100,12 @@ void NcrSetStatsMode(RenderContext* ctx, int mode) {
 
 unsigned long long NcrKernelLaunchCount(void) { return g_launches.load(); }
 
+double NcrMeasureF64Rate(void) {
+    if (!use_device()) return 0.0;
+    g_launches += 2;
+    return ncr_measure_f64_rate(0);
+}
+
 int NcrRerunLastFlush(RenderContext* ctx, int iters, int flush_l2, float* ms_out) {
     NcrContext* c = live(ctx);
     if (!c || !c->has_last || !use_device()) return -1;

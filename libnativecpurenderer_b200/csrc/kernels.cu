@@ -207,3 +207,48 @@ extern "C" void ncr_launch_resample(const NcrCmd* src, void* out, int ow, int oh
     dim3 grid((ow + 15) / 16, (oh + 15) / 16);
     ncr_resample<<<grid, 256, 0, s>>>(*src, out, ow, oh);
 }
+
+// ------------------------------------------------------------------------------------------------
+// measurement aid: the rate of NON-FUSED f64 multiplies and adds (what this path is made of — FMA contraction is
+// forbidden by the bit-exactness contract).  8 independent mul->add chains per thread, 8 warps per SM sub-partition.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ncr_f64_rate(double* out, int iters, double m, double a) {
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (double)(threadIdx.x + k);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = ADD(MUL(v[k], m), a);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s = ADD(s, v[k]);
+    if (s == 12345.678) out[0] = s;   // keeps the chains alive; never true for the operands used
+}
+
+// Returns f64 instructions per second (DMUL + DADD, each counted once), 0 on failure.
+extern "C" double ncr_measure_f64_rate(cudaStream_t s) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double* d = nullptr;
+    if (cudaMalloc(&d, 8) != cudaSuccess) return 0.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int iters = 20000, blocks = sms * 8;
+    ncr_f64_rate<<<blocks, 256, 0, s>>>(d, 2000, 1.0000001, 1e-9);   // warm-up
+    cudaEventRecord(e0, s);
+    ncr_f64_rate<<<blocks, 256, 0, s>>>(d, iters, 1.0000001, 1e-9);
+    cudaEventRecord(e1, s);
+    double rate = 0.0;
+    if (cudaStreamSynchronize(s) == cudaSuccess) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        rate = (double)blocks * 256.0 * iters * 16.0 / (ms * 1e-3);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    return rate;
+}

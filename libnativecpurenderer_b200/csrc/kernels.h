@@ -16,4 +16,5 @@ void ncr_launch_flush(const NcrFlushArgs* A, cudaStream_t s, cudaEvent_t* ev);
 void ncr_launch_composite(const NcrFlushArgs* A, cudaStream_t s);
 void ncr_launch_convert_u8(const double* fb, unsigned char* out, size_t n, cudaStream_t s);
 void ncr_launch_resample(const NcrCmd* src, void* out, int ow, int oh, cudaStream_t s);
+double ncr_measure_f64_rate(cudaStream_t s);   // non-fused DMUL+DADD instructions per second
 }
