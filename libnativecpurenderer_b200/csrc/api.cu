@@ -380,8 +380,17 @@ bool reserve_cmd(NcrContext* c, size_t extra_aux) {
     return true;
 }
 
-const unsigned long long kMaxPendingEntries = 48ull << 20;   // tile-list entries (4 B each) before an early submit
-const size_t kMaxPendingCmds = 1u << 20;
+// A batch is submitted early (asynchronously; recording continues in the other staging buffer) once it holds this many
+// commands or tile-list entries.  NCR_MAX_PENDING_CMDS / NCR_MAX_PENDING_ENTRIES override the defaults (tests use tiny
+// values to exercise mid-stream submits).
+size_t env_limit(const char* name, size_t dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    const long long n = atoll(v);
+    return n > 0 ? (size_t)n : dflt;
+}
+const unsigned long long kMaxPendingEntries = env_limit("NCR_MAX_PENDING_ENTRIES", 48ull << 20);   // 4 B each
+const size_t kMaxPendingCmds = env_limit("NCR_MAX_PENDING_CMDS", 1u << 20);
 
 // Starts a command covering the pixel box [l,r) x [t,b) (already clamped to the canvas).  Returns nullptr when
 // the box is empty — no pixel can be touched, so nothing is recorded.

@@ -24,6 +24,17 @@
 #define FULL 0xffffffffu
 #define NCR_LUT_COPIES 16
 #define NCR_COMPOSITE_THREADS 128
+// Pixel slots per lane: NCR_NX columns x 2 rows of 8x4 blocks.  NX=2: a warp owns a 16x8 half-tile (4 px per lane);
+// NX=1: an 8x8 quarter-tile (2 px per lane: half the register state, twice the warps per tile).
+#ifndef NCR_NX
+#define NCR_NX 2
+#endif
+#define NCR_NY 2
+#define NCR_P (NCR_NX * NCR_NY)
+#define NCR_RW (8 * NCR_NX)                      // region width in pixels
+#define NCR_TASKS_PER_TILE ((16 / NCR_RW) * 2)   // regions per 16x16 tile
+#define SX(p) ((p) % NCR_NX)
+#define SY(p) ((p) / NCR_NX)
 #ifndef NCR_COMPOSITE_MIN_CTAS
 #define NCR_COMPOSITE_MIN_CTAS 3
 #endif
@@ -158,7 +169,13 @@ __device__ __forceinline__ double lut_byte(uint32_t base, uint32_t texel) {
     return v;
 }
 
-#define FOR4 _Pragma("unroll") for (int p = 0; p < 4; ++p)
+#define FOR4 _Pragma("unroll") for (int p = 0; p < NCR_P; ++p)
+
+__device__ __forceinline__ bool any_slot(const bool (&in)[NCR_P]) {
+    bool r = false;
+    FOR4 r = r || in[p];
+    return r;
+}
 
 // Exact rejection of a command against a block of pixels [i0,i1] x [j0,j1] (inclusive), for the ops whose coverage is the
 // four inclusive bounds of cpp:765-768 on the inverse-mapped position.
@@ -189,20 +206,20 @@ __device__ __forceinline__ bool quad_misses_region(const NcrCmd* __restrict__ c,
 
 // Per-lane pixel slots of the current half-tile.
 struct Slots {
-    int xs[2], ys[2];        // pixel columns / rows owned by this lane
-    double fx[2], fy[2];     // the same as f64 (int -> f64 is exact)
+    int xs[NCR_NX], ys[NCR_NY];        // pixel columns / rows owned by this lane
+    double fx[NCR_NX], fy[NCR_NY];     // the same as f64 (int -> f64 is exact)
 };
 
 // Shared tail of the textured ops: decode four RGBA8 texels and blend (straight-line, predicated).  RGB_ONE: the colour
 // transform's rgb are exactly 1.0, so r * 1.0 (cpp:525-527) is the identity and is not issued.
 template <bool ALPHA, bool COUNT, bool RGB_ONE>
-__device__ __forceinline__ void shade_rgba8(const NcrCmd& c, uint32_t lut_base, const uint32_t (&tx)[4], const bool (&in)[4],
-                                            double (&dr)[4], double (&dg)[4], double (&db)[4], double (&da)[4],
+__device__ __forceinline__ void shade_rgba8(const NcrCmd& c, uint32_t lut_base, const uint32_t (&tx)[NCR_P], const bool (&in)[NCR_P],
+                                            double (&dr)[NCR_P], double (&dg)[NCR_P], double (&db)[NCR_P], double (&da)[NCR_P],
                                             unsigned long long& n_applied) {
     const double ct3 = c.ct[3];
     double ct0 = 1.0, ct1 = 1.0, ct2 = 1.0;
     if (!RGB_ONE) { ct0 = c.ct[0]; ct1 = c.ct[1]; ct2 = c.ct[2]; }
-    bool opaque[4];
+    bool opaque[NCR_P];
     FOR4 {
         opaque[p] = false;
 #ifdef NCR_SLOT_SKIP
@@ -216,7 +233,7 @@ __device__ __forceinline__ void shade_rgba8(const NcrCmd& c, uint32_t lut_base, 
         opaque[p] = blend<ALPHA>(dr[p], dg[p], db[p], da[p], r, g, b, a, in[p]);
         if (COUNT) n_applied += in[p] ? 1 : 0;
     }
-    if (__any_sync(FULL, opaque[0] || opaque[1] || opaque[2] || opaque[3])) {   // a == 1: the source is stored as is
+    if (__any_sync(FULL, any_slot(opaque))) {   // a == 1: the source is stored as is
         FOR4 {
             const uint32_t t = tx[p];
             double r = lut_byte<0>(lut_base, t), g = lut_byte<1>(lut_base, t), b = lut_byte<2>(lut_base, t);
@@ -231,24 +248,27 @@ __device__ __forceinline__ void shade_rgba8(const NcrCmd& c, uint32_t lut_base, 
 // slots), so the f64 dependency chains of the slots interleave.
 template <bool ALPHA, bool COUNT>
 __device__ __forceinline__ void tex_fast(const NcrCmd& c, const uint32_t op, const uint32_t flags, const Slots& S,
-                                         const double* lut, uint32_t lut_base, bool (&in)[4], double (&dr)[4], double (&dg)[4],
-                                         double (&db)[4], double (&da)[4], unsigned long long& n_applied) {
+                                         const double* lut, uint32_t lut_base, bool (&in)[NCR_P], double (&dr)[NCR_P], double (&dg)[NCR_P],
+                                         double (&db)[NCR_P], double (&da)[NCR_P], unsigned long long& n_applied) {
     // TransformPointFromMatrix(inv, i, j), cpp:451-452: (inv0*i + inv2*j) + inv4.  inv0*i depends only on the pixel
     // column and inv2*j only on the row: each product is formed once per lane.
     const double i0 = c.inv[0], i1 = c.inv[1], i2 = c.inv[2], i3 = c.inv[3], i4 = c.inv[4], i5 = c.inv[5];
-    const double ax[2] = {MUL(i0, S.fx[0]), MUL(i0, S.fx[1])}, bx[2] = {MUL(i1, S.fx[0]), MUL(i1, S.fx[1])};
-    const double ay[2] = {MUL(i2, S.fy[0]), MUL(i2, S.fy[1])}, by[2] = {MUL(i3, S.fy[0]), MUL(i3, S.fy[1])};
+    double ax[NCR_NX], bx[NCR_NX], ay[NCR_NY], by[NCR_NY];
+#pragma unroll
+    for (int k = 0; k < NCR_NX; ++k) { ax[k] = MUL(i0, S.fx[k]); bx[k] = MUL(i1, S.fx[k]); }
+#pragma unroll
+    for (int k = 0; k < NCR_NY; ++k) { ay[k] = MUL(i2, S.fy[k]); by[k] = MUL(i3, S.fy[k]); }
     const double cx = c.x, cy = c.y, cxw = c.xw, cyh = c.yh, sx = c.sx, sy = c.sy;
-    double u[4], v[4];
+    double u[NCR_P], v[NCR_P];
     FOR4 {
-        const double X = ADD(ADD(ax[p & 1], ay[p >> 1]), i4);
-        const double Y = ADD(ADD(bx[p & 1], by[p >> 1]), i5);
+        const double X = ADD(ADD(ax[SX(p)], ay[SY(p)]), i4);
+        const double Y = ADD(ADD(bx[SX(p)], by[SY(p)]), i5);
         // the four inclusive bounds, cpp:765-768 (NaN compares false on both sides, as in C)
         in[p] = in[p] && !(X < cx) && !(X > cxw) && !(Y < cy) && !(Y > cyh);
         u[p] = MUL(SUB(X, cx), sx);   // cpp:770-771
         v[p] = MUL(SUB(Y, cy), sy);
     }
-    if (!__any_sync(FULL, in[0] || in[1] || in[2] || in[3])) return;
+    if (!__any_sync(FULL, any_slot(in))) return;
     if (op == NCR_OP_TEX_SPLIT) {
         // cpp:812-813: u = (uStart + (uEnd - uStart) * u / tex->width) * tex->width
         const double uS = c.p[0], dU = c.p[1], vS = c.p[2], dV = c.p[3], fw = c.p[4], fh = c.p[5];
@@ -271,7 +291,7 @@ __device__ __forceinline__ void tex_fast(const NcrCmd& c, const uint32_t op, con
     // u >= w-1 iff trunc(u) >= w-1 (cvt.rzi saturates, so huge u stays >= w-1).
     const int tw = c.tex_w, th = c.tex_h;
     const uint32_t* t32 = (const uint32_t*)c.tex;
-    uint32_t tx[4];
+    uint32_t tx[NCR_P];
     FOR4 {
         int xi = __double2int_rz(u[p]), yi = __double2int_rz(v[p]);
         xi = xi >= tw - 1 ? tw - 2 : xi;
@@ -287,16 +307,19 @@ __device__ __forceinline__ void tex_fast(const NcrCmd& c, const uint32_t op, con
 // One command applied to the warp's 128 pixels.  `c` lives in shared memory (warp-uniform reads: one wavefront each).
 template <bool ALPHA, bool COUNT>
 __device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A, const Slots& S, const double* lut /* + lane&15 */, uint32_t lut_base,
-                                          double (&dr)[4], double (&dg)[4], double (&db)[4], double (&da)[4],
+                                          double (&dr)[NCR_P], double (&dg)[NCR_P], double (&db)[NCR_P], double (&da)[NCR_P],
                                           unsigned long long& n_applied) {
     const uint32_t op = c.op, flags = c.flags;
     // pixel-box membership: the reference's loop bounds (boxes are clamped to the canvas on the host, so a pixel slot
     // outside the canvas is never inside a box).  (unsigned)(v - lo) < (unsigned)(hi - lo)  <=>  lo <= v < hi.
     const unsigned wx = (unsigned)(c.r - c.l), wy = (unsigned)(c.b - c.t);
-    const bool inx[2] = {(unsigned)(S.xs[0] - c.l) < wx, (unsigned)(S.xs[1] - c.l) < wx};
-    const bool iny[2] = {(unsigned)(S.ys[0] - c.t) < wy, (unsigned)(S.ys[1] - c.t) < wy};
-    bool in[4];
-    FOR4 in[p] = inx[p & 1] && iny[p >> 1];
+    bool inx[NCR_NX], iny[NCR_NY];
+#pragma unroll
+    for (int k = 0; k < NCR_NX; ++k) inx[k] = (unsigned)(S.xs[k] - c.l) < wx;
+#pragma unroll
+    for (int k = 0; k < NCR_NY; ++k) iny[k] = (unsigned)(S.ys[k] - c.t) < wy;
+    bool in[NCR_P];
+    FOR4 in[p] = inx[SX(p)] && iny[SY(p)];
 
     if (flags & NCR_F_FAST_AFFINE) {   // DrawTexture / DrawSplittedTexture on RGBA8, nearest: the hot case, tested first
         tex_fast<ALPHA, COUNT>(c, op, flags, S, lut, lut_base, in, dr, dg, db, da, n_applied);
@@ -309,7 +332,7 @@ __device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A
             if (ALPHA) da[p] = c.p[3];
             // 3-channel canvas, non-uniform colour: SetPixel's index+3 store (cpp:510) leaves `a` in the red of pixel
             // (0, j>=1), because column 0 is written first and the last column of the previous row spills into it.
-            else if ((flags & NCR_F_RGB_SPILL) && S.xs[p & 1] == 0 && S.ys[p >> 1] >= 1 && A.d.w > 1) dr[p] = c.p[3];
+            else if ((flags & NCR_F_RGB_SPILL) && S.xs[SX(p)] == 0 && S.ys[SY(p)] >= 1 && A.d.w > 1) dr[p] = c.p[3];
         }
         return;
     }
@@ -325,14 +348,17 @@ __device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A
     }
 
     // inverse-mapped source position, TransformPointFromMatrix(inv, i, j), cpp:451-452: (inv0*i + inv2*j) + inv4.
-    double X[4], Y[4];
+    double X[NCR_P], Y[NCR_P];
     if (op != NCR_OP_FILL_COLOR && op != NCR_OP_APPLY_PIXEL && op != NCR_OP_TEX_IDENT && op != NCR_OP_TEX_PERSP) {
-        const double ax[2] = {MUL(c.inv[0], S.fx[0]), MUL(c.inv[0], S.fx[1])}, bx[2] = {MUL(c.inv[1], S.fx[0]), MUL(c.inv[1], S.fx[1])};
-        const double ay[2] = {MUL(c.inv[2], S.fy[0]), MUL(c.inv[2], S.fy[1])}, by[2] = {MUL(c.inv[3], S.fy[0]), MUL(c.inv[3], S.fy[1])};
+        double ax[NCR_NX], bx[NCR_NX], ay[NCR_NY], by[NCR_NY];
+#pragma unroll
+        for (int k = 0; k < NCR_NX; ++k) { ax[k] = MUL(c.inv[0], S.fx[k]); bx[k] = MUL(c.inv[1], S.fx[k]); }
+#pragma unroll
+        for (int k = 0; k < NCR_NY; ++k) { ay[k] = MUL(c.inv[2], S.fy[k]); by[k] = MUL(c.inv[3], S.fy[k]); }
         const double i4 = c.inv[4], i5 = c.inv[5];
         FOR4 {
-            X[p] = ADD(ADD(ax[p & 1], ay[p >> 1]), i4);
-            Y[p] = ADD(ADD(bx[p & 1], by[p >> 1]), i5);
+            X[p] = ADD(ADD(ax[SX(p)], ay[SY(p)]), i4);
+            Y[p] = ADD(ADD(bx[SX(p)], by[SY(p)]), i5);
         }
         if (op != NCR_OP_CIRCLE && op != NCR_OP_POLY) {
             // the four inclusive bounds, cpp:765-768 (NaN compares false on both sides, as in C)
@@ -343,7 +369,7 @@ __device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A
 
     if (op == NCR_OP_GRAD) {   // cpp:1308-1313; p[4..7] = bottom - top
         const double hgt = c.sy, cy = c.y;
-        if (!__any_sync(FULL, in[0] || in[1] || in[2] || in[3])) return;
+        if (!__any_sync(FULL, any_slot(in))) return;
         FOR4 {
             const double t = DIV(SUB(Y[p], cy), hgt);
             const double r = MUL(ADD(c.p[0], MUL(c.p[4], t)), c.ct[0]);
@@ -393,17 +419,17 @@ __device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A
 
     // ---- textured ops: DrawTexture (both paths), DrawSplittedTexture, perspective extension ----
     const int tw = c.tex_w, th = c.tex_h;
-    double u[4], v[4];
+    double u[NCR_P], v[NCR_P];
     if (op == NCR_OP_TEX_IDENT) {   // cpp:741-745: pixels i >= (i64)x with (f64)i < x + width; u = (i - x) * scaleX
         FOR4 {
-            const double fi = S.fx[p & 1], fj = S.fy[p >> 1];
+            const double fi = S.fx[SX(p)], fj = S.fy[SY(p)];
             in[p] = in[p] && fi >= c.p[0] && fi < c.xw && fj >= c.p[1] && fj < c.yh;
             u[p] = MUL(SUB(fi, c.x), c.sx);
             v[p] = MUL(SUB(fj, c.y), c.sy);
         }
     } else if (op == NCR_OP_TEX_PERSP) {   // extension: row-major 3x3 inverse homography, then cpp:765-771
         FOR4 {
-            const double fi = S.fx[p & 1], fj = S.fy[p >> 1];
+            const double fi = S.fx[SX(p)], fj = S.fy[SY(p)];
             const double hw = ADD(ADD(MUL(c.p[0], fi), MUL(c.p[1], fj)), c.p[2]);
             const double Xp = DIV(ADD(ADD(MUL(c.inv[0], fi), MUL(c.inv[1], fj)), c.inv[2]), hw);
             const double Yp = DIV(ADD(ADD(MUL(c.inv[3], fi), MUL(c.inv[4], fj)), c.inv[5]), hw);
@@ -438,7 +464,7 @@ __device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A
 
     if (flags & NCR_F_TEX_FAST) {   // RGBA8 texels, nearest, < 2^31 texels (clamp-after-truncate: see tex_fast)
         const uint32_t* t32 = (const uint32_t*)c.tex;
-        uint32_t tx[4];
+        uint32_t tx[NCR_P];
         FOR4 {
             int xi = __double2int_rz(u[p]), yi = __double2int_rz(v[p]);
             xi = xi >= tw - 1 ? tw - 2 : xi;
@@ -477,7 +503,7 @@ __global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, NCR_COMPOSITE_MIN_CTAS)
     const uint32_t lut_base = (uint32_t)__cvta_generic_to_shared(lut);
     const int lx = lane & 7, ly = lane >> 3;
     const int n_tiles = A.d.tiles_x * A.d.tiles_y;
-    const int n_tasks = n_tiles * 2;
+    const int n_tasks = n_tiles * NCR_TASKS_PER_TILE;
     constexpr int IPP = ALPHA ? 4 : 3;
     constexpr uint32_t WORDS = NCR_CMD_WORDS16;   // 15 x 16 B
     const int W = A.d.w, H = A.d.h;
@@ -488,28 +514,28 @@ __global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, NCR_COMPOSITE_MIN_CTAS)
         if (lane == 0) task = (int)atomicAdd(&A.cursors[5], 1u);
         task = __shfl_sync(FULL, task, 0);
         if (task >= n_tasks) break;
-        const int tile = task >> 1;
+        const int tile = task / NCR_TASKS_PER_TILE, sub = task % NCR_TASKS_PER_TILE;
         const uint32_t loff = __ldg(&A.fine_off[tile]);
         const uint32_t lcount = __ldg(&A.fine_off[n_tiles + tile]);
         if (lcount == 0 && A.u8_out == nullptr) continue;
 
-        const int x0 = (tile % A.d.tiles_x) * NCR_TILE;
-        const int y0 = (tile / A.d.tiles_x) * NCR_TILE + (task & 1) * 8;
-        if (y0 >= H) continue;
+        const int x0 = (tile % A.d.tiles_x) * NCR_TILE + (sub % (16 / NCR_RW)) * NCR_RW;
+        const int y0 = (tile / A.d.tiles_x) * NCR_TILE + (sub / (16 / NCR_RW)) * 8;
+        if (y0 >= H || x0 >= W) continue;
         Slots S;
-        S.xs[0] = x0 + lx; S.xs[1] = x0 + 8 + lx;
-        S.ys[0] = y0 + ly; S.ys[1] = y0 + 4 + ly;
-        S.fx[0] = (double)S.xs[0]; S.fx[1] = (double)S.xs[1];
-        S.fy[0] = (double)S.ys[0]; S.fy[1] = (double)S.ys[1];
-        bool valid[4];
-        FOR4 valid[p] = S.xs[p & 1] < W && S.ys[p >> 1] < H;
+#pragma unroll
+        for (int k = 0; k < NCR_NX; ++k) { S.xs[k] = x0 + 8 * k + lx; S.fx[k] = (double)S.xs[k]; }
+#pragma unroll
+        for (int k = 0; k < NCR_NY; ++k) { S.ys[k] = y0 + 4 * k + ly; S.fy[k] = (double)S.ys[k]; }
+        bool valid[NCR_P];
+        FOR4 valid[p] = S.xs[SX(p)] < W && S.ys[SY(p)] < H;
 
-        double dr[4], dg[4], db[4], da[4];
+        double dr[NCR_P], dg[NCR_P], db[NCR_P], da[NCR_P];
         FOR4 { dr[p] = 0.0; dg[p] = 0.0; db[p] = 0.0; da[p] = 0.0; }
         // The canvas is read unless the list starts with a SetColor (then every pixel is overwritten first).
         if (A.load_fb != 0 || lcount == 0) {
             FOR4 if (valid[p]) {
-                const double* q = A.fb + ((size_t)S.ys[p >> 1] * W + S.xs[p & 1]) * IPP;
+                const double* q = A.fb + ((size_t)S.ys[SY(p)] * W + S.xs[SX(p)]) * IPP;
                 if (ALPHA) {
                     const double2 lo = ((const double2*)q)[0], hi = ((const double2*)q)[1];
                     dr[p] = lo.x; dg[p] = lo.y; db[p] = hi.x; da[p] = hi.y;
@@ -529,8 +555,8 @@ __global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, NCR_COMPOSITE_MIN_CTAS)
                 if (k0 + lane < lcount) {
                     mine = __ldg(&A.fine_list[loff + k0 + lane]);
                     const int4 box = __ldg((const int4*)&A.boxes[mine]);   // l, r, t, b
-                    hit = box.z < y0 + 8 && box.w > y0;
-                    if (hit) hit = !quad_misses_region(A.cmds + mine, max(x0, box.x), min(x0 + NCR_TILE, box.y) - 1,
+                    hit = box.z < y0 + 8 && box.w > y0 && box.x < x0 + NCR_RW && box.y > x0;
+                    if (hit) hit = !quad_misses_region(A.cmds + mine, max(x0, box.x), min(x0 + NCR_RW, box.y) - 1,
                                                        max(y0, box.z), min(y0 + 8, box.w) - 1);
                 }
                 pending = __ballot_sync(FULL, hit);
@@ -560,7 +586,7 @@ __global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, NCR_COMPOSITE_MIN_CTAS)
 
         // tile write-back: canonical f64 canvas (only if something was drawn) and the fused (iu8)(v*255) image
         FOR4 if (valid[p]) {
-            const size_t pix = ((size_t)S.ys[p >> 1] * W + S.xs[p & 1]) * IPP;
+            const size_t pix = ((size_t)S.ys[SY(p)] * W + S.xs[SX(p)]) * IPP;
             if (lcount != 0) {
                 double* q = A.fb + pix;
                 if (ALPHA) {
@@ -574,7 +600,7 @@ __global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, NCR_COMPOSITE_MIN_CTAS)
                 if (ALPHA) {
                     const uint32_t o = (uint32_t)ncr_to_u8(dr[p]) | ((uint32_t)ncr_to_u8(dg[p]) << 8) |
                                        ((uint32_t)ncr_to_u8(db[p]) << 16) | ((uint32_t)ncr_to_u8(da[p]) << 24);
-                    ((uint32_t*)A.u8_out)[(size_t)S.ys[p >> 1] * W + S.xs[p & 1]] = o;
+                    ((uint32_t*)A.u8_out)[(size_t)S.ys[SY(p)] * W + S.xs[SX(p)]] = o;
                 } else {
                     unsigned char* o = A.u8_out + pix;
                     o[0] = ncr_to_u8(dr[p]); o[1] = ncr_to_u8(dg[p]); o[2] = ncr_to_u8(db[p]);
@@ -600,7 +626,7 @@ void launch(const NcrFlushArgs& A, cudaStream_t s, int slot) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ncr_composite<ALPHA, COUNT>, NCR_COMPOSITE_THREADS, 0);
         g_grid[slot] = sms * (per_sm > 0 ? per_sm : 1);   // persistent: every resident CTA slot, one wave
     }
-    const int n_tasks = A.d.tiles_x * A.d.tiles_y * 2;
+    const int n_tasks = A.d.tiles_x * A.d.tiles_y * NCR_TASKS_PER_TILE;
     const int warps = NCR_COMPOSITE_THREADS / 32;
     int grid = g_grid[slot];
     if (grid * warps > n_tasks) grid = (n_tasks + warps - 1) / warps;

@@ -277,3 +277,75 @@ def test_clip_rect_limits_every_draw_kind(gpu):
     img = ctx.get_buffer_np().reshape(48, 64, 4)
     touched = img[..., 3] != 0
     assert touched[8:24, 10:30].all() and touched.sum() == 20 * 16
+
+
+# ---- host runtime behaviour ------------------------------------------------------------------------------------------
+def test_early_submits_do_not_change_the_image(image_rgba, port):
+    """With tiny batch limits (NCR_MAX_PENDING_CMDS) every few draws are submitted on their own, asynchronously, while
+    recording continues in the other staging buffer: the result must still be the restatement's, bit for bit."""
+    import os
+    import subprocess
+    import sys
+    import json
+
+    from conftest import ROOT
+
+    want = cases.make_random_case(511)(port, image_rgba)
+    code = (
+        "import sys, json; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import numpy as np, cases\n"
+        "from libnativecpurenderer_b200.binding import Renderer\n"
+        "img = np.load(%r)['rgba']\n"
+        "print(json.dumps(cases.make_random_case(511)(Renderer(), img)))\n"
+        % (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden", "image_rgba.npz"))
+    )
+    for limit in ("3", "17"):
+        env = dict(os.environ, NCR_MAX_PENDING_CMDS=limit)
+        res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+        assert res.returncode == 0, res.stderr
+        assert json.loads(res.stdout.strip().splitlines()[-1]) == want
+
+
+def test_contexts_on_concurrent_threads_are_independent(gpu, image_rgba):
+    """One context per thread (ctypes releases the GIL): each thread's frames equal the single-threaded render."""
+    import threading
+
+    tex_np = streams.make_c2_textures()
+    tex = [gpu.Texture.from_numpy(t) for t in tex_np]
+
+    def render(seed):
+        ctx = gpu.RenderContext(320, 180, True)
+        out = []
+        for f in range(3):
+            streams.stream_c2(ctx, tex, n=150, seed=seed + f)
+            out.append(hashlib.sha1(bytes(ctx.get_buffer_as_uint8())).hexdigest())
+        return out
+
+    want = {s: render(s) for s in (10, 20, 30, 40)}
+    got = {}
+    threads = [threading.Thread(target=lambda s=s: got.__setitem__(s, render(s))) for s in want]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert got == want
+
+
+def test_stale_and_null_handles_are_ignored_not_dereferenced(gpu, image_rgba):
+    lib = gpu.lib
+    ctx = gpu.RenderContext(16, 16, True)
+    tex = gpu.Texture.from_numpy(image_rgba)
+    ptr, tptr = ctx._ptr, tex._ptr
+    ctx.set_color(.5, .5, .5, .5)
+    lib.DrawTexture(ptr, None, 0.0, 0.0, 4.0, 4.0)          # NULL texture: no-op
+    lib.DestroyTexture(tptr)
+    tex._ptr = 0
+    lib.DrawTexture(ptr, tptr, 0.0, 0.0, 4.0, 4.0)          # destroyed texture: detected, no-op
+    assert lib.GetTextureWidth(tptr) == 0
+    assert set(ctx.get_buffer_as_uint8()) == {127}
+    lib.DestroyRenderContext(ptr)
+    ctx._ptr = 0
+    assert lib.GetBufferSize(ptr) == 0                        # destroyed context: detected
+    lib.DrawRect(ptr, 0.0, 0.0, 4.0, 4.0, 1.0, 1.0, 1.0, 1.0)
+    lib.DestroyRenderContext(ptr)                             # double destroy: harmless
+    assert lib.GetBufferSize(None) == 0
