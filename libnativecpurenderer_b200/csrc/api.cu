@@ -444,7 +444,9 @@ bool is_pow2(i64 v) { return v > 0 && (v & (v - 1)) == 0; }
 
 // Texture operand of a draw.  Aliases of a canvas (cpp:377-384) are resolved to a snapshot of that canvas as of
 // this call, which is what an immediate-mode read of the shared buffer would have seen.
-bool bind_texture(NcrTexture* tex, const void** ptr, uint32_t* flags, DevRef* keep) {
+// `keep` points at the reference that must outlive the recorded command: the texture's own buffer (no copy, hence no
+// atomic reference-count traffic on the draw path) or, for an alias, the snapshot stored in `snap_store`.
+bool bind_texture(NcrTexture* tex, const void** ptr, uint32_t* flags, DevRef* snap_store, const DevRef** keep) {
     if (tex->alias) {
         NcrContext* src = live(tex->alias);
         if (!src) return false;
@@ -454,12 +456,13 @@ bool bind_texture(NcrTexture* tex, const void** ptr, uint32_t* flags, DevRef* ke
         if (!snap) return false;
         if (!CK(cudaMemcpy(snap->p, src->fb->p, bytes, cudaMemcpyDeviceToDevice))) return false;
         *ptr = snap->p;
-        *keep = snap;
+        *snap_store = snap;
+        *keep = snap_store;
         *flags = NCR_F_TEX_F64 | (src->alpha ? NCR_F_TEX_ALPHA : 0);
         return true;
     }
     *ptr = tex->buf->p;
-    *keep = tex->buf;
+    *keep = &tex->buf;
     *flags = (tex->is_f64 ? NCR_F_TEX_F64 : 0) | (tex->alpha ? NCR_F_TEX_ALPHA : 0);
     return true;
 }
@@ -474,8 +477,13 @@ void tex_dims(NcrTexture* tex, i64* w, i64* h) {
     }
 }
 
+// Keeps the texels alive until the batch retires.  A frame uses few distinct textures: the recent ones are found by
+// pointer comparison, so the shared_ptr is copied (one atomic increment) once per texture per batch, not per draw.
 void keep_ref(NcrContext* c, const DevRef& r) {
-    if (c->refs.empty() || c->refs.back() != r) c->refs.push_back(r);
+    const size_t n = c->refs.size();
+    for (size_t k = n > 16 ? n - 16 : 0; k < n; ++k)
+        if (c->refs[k].get() == r.get()) return;
+    c->refs.push_back(r);
 }
 
 NcrTexture* new_texture(i64 w, i64 h, bool alpha, bool is_f64, const void* host_data) {
@@ -493,10 +501,13 @@ NcrTexture* new_texture(i64 w, i64 h, bool alpha, bool is_f64, const void* host_
 
 // Materialises a texture operand for setup-time consumers (resample, hit-effect mask): alias -> snapshot.
 bool texture_view(NcrTexture* tex, NcrCmd* view, DevRef* keep) {
+    const DevRef* which = nullptr;
+    DevRef snap;
     memset(view, 0, sizeof(*view));
     const void* p = nullptr;
     uint32_t flags = 0;
-    if (!bind_texture(tex, &p, &flags, keep)) return false;
+    if (!bind_texture(tex, &p, &flags, &snap, &which)) return false;
+    *keep = *which;
     i64 w, h;
     tex_dims(tex, &w, &h);
     view->tex = p;
@@ -765,7 +776,7 @@ void DrawTexture(RenderContext* ctx, Texture* tex_, double x, double y, double w
     i64 tw, th;
     tex_dims(tex, &tw, &th);
     const double scaleX = tw / width, scaleY = th / height;   // cpp:728-729
-    const void* ptr; uint32_t tflags; DevRef keep;
+    const void* ptr; uint32_t tflags; DevRef snap; const DevRef* keep = nullptr;
     if (ncr_is_no_transform(c->st.m)) {
         // cpp:741-742: for (i64 i = x; i < x + width; ++i) — the matrix is ignored, ApplyPixel clips.
         const i64 i0 = ncr_trunc_i64(x), j0 = ncr_trunc_i64(y);
@@ -775,10 +786,10 @@ void DrawTexture(RenderContext* ctx, Texture* tex_, double x, double y, double w
         const i64 r = !(cr > 0) ? 0 : (cr >= (double)c->w ? c->w : (i64)cr);
         const i64 b = !(cb > 0) ? 0 : (cb >= (double)c->h ? c->h : (i64)cb);
         if (l >= r || t >= b) return;
-        if (!bind_texture(tex, &ptr, &tflags, &keep)) return;
+        if (!bind_texture(tex, &ptr, &tflags, &snap, &keep)) return;
         NcrCmd* cmd = begin_cmd(c, NCR_OP_TEX_IDENT, l, r, t, b);
         if (!cmd) return;
-        fill_texture_fields(c, cmd, ptr, tflags, keep, tw, th);
+        fill_texture_fields(c, cmd, ptr, tflags, *keep, tw, th);
         cmd->x = x; cmd->y = y; cmd->xw = xw; cmd->yh = yh;
         cmd->sx = scaleX; cmd->sy = scaleY;
         cmd->p[0] = (double)i0; cmd->p[1] = (double)j0;
@@ -787,10 +798,10 @@ void DrawTexture(RenderContext* ctx, Texture* tex_, double x, double y, double w
     i64 l, r, t, b;
     ncr_border(c->st.m, x, y, width, height, c->w, c->h, &l, &r, &t, &b);
     if (l >= r || t >= b) return;
-    if (!bind_texture(tex, &ptr, &tflags, &keep)) return;
+    if (!bind_texture(tex, &ptr, &tflags, &snap, &keep)) return;
     NcrCmd* cmd = begin_cmd(c, NCR_OP_TEX, l, r, t, b);
     if (!cmd) return;
-    fill_texture_fields(c, cmd, ptr, tflags, keep, tw, th);
+    fill_texture_fields(c, cmd, ptr, tflags, *keep, tw, th);
     put_inverse(c, cmd);
     cmd->x = x; cmd->y = y; cmd->xw = x + width; cmd->yh = y + height;
     cmd->sx = scaleX; cmd->sy = scaleY;
@@ -807,11 +818,11 @@ void DrawSplittedTexture(RenderContext* ctx, Texture* tex_, double x, double y, 
     i64 l, r, t, b;
     ncr_border(c->st.m, x, y, width, height, c->w, c->h, &l, &r, &t, &b);
     if (l >= r || t >= b) return;
-    const void* ptr; uint32_t tflags; DevRef keep;
-    if (!bind_texture(tex, &ptr, &tflags, &keep)) return;
+    const void* ptr; uint32_t tflags; DevRef snap; const DevRef* keep = nullptr;
+    if (!bind_texture(tex, &ptr, &tflags, &snap, &keep)) return;
     NcrCmd* cmd = begin_cmd(c, NCR_OP_TEX_SPLIT, l, r, t, b);
     if (!cmd) return;
-    fill_texture_fields(c, cmd, ptr, tflags, keep, tw, th);
+    fill_texture_fields(c, cmd, ptr, tflags, *keep, tw, th);
     put_inverse(c, cmd);
     cmd->x = x; cmd->y = y; cmd->xw = x + width; cmd->yh = y + height;
     cmd->sx = tw / width; cmd->sy = th / height;   // cpp:793-794
@@ -1177,12 +1188,12 @@ void NcrDrawTexturePerspective(RenderContext* ctx, Texture* tex_, const double i
     if (width == 0 || height == 0) return;
     i64 tw, th;
     tex_dims(tex, &tw, &th);
-    const void* ptr; uint32_t tflags; DevRef keep;
-    if (!bind_texture(tex, &ptr, &tflags, &keep)) return;
+    const void* ptr; uint32_t tflags; DevRef snap; const DevRef* keep = nullptr;
+    if (!bind_texture(tex, &ptr, &tflags, &snap, &keep)) return;
     // No forward map is available for a general projective inverse: cover the canvas (or the clip rect).
     NcrCmd* cmd = begin_cmd(c, NCR_OP_TEX_PERSP, 0, c->w, 0, c->h);
     if (!cmd) return;
-    fill_texture_fields(c, cmd, ptr, tflags, keep, tw, th);
+    fill_texture_fields(c, cmd, ptr, tflags, *keep, tw, th);
     for (int k = 0; k < 6; ++k) cmd->inv[k] = inv_h[k];
     cmd->p[0] = inv_h[6]; cmd->p[1] = inv_h[7]; cmd->p[2] = inv_h[8];
     cmd->x = x; cmd->y = y; cmd->xw = x + width; cmd->yh = y + height;
