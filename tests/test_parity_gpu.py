@@ -349,3 +349,36 @@ def test_stale_and_null_handles_are_ignored_not_dereferenced(gpu, image_rgba):
     lib.DrawRect(ptr, 0.0, 0.0, 4.0, 4.0, 1.0, 1.0, 1.0, 1.0)
     lib.DestroyRenderContext(ptr)                             # double destroy: harmless
     assert lib.GetBufferSize(None) == 0
+
+
+def _full_size_vs_cpu(gpu, cpu, workload):
+    """The bench's exact workload (bench.build_workload) on both libraries through the C replayer; u8 + f64 digests."""
+    import sys
+
+    from conftest import REPLAY_LIB, ROOT
+
+    sys.path.insert(0, ROOT)
+    import bench
+
+    w, h, alpha, tex_np, arr, draws, full = bench.build_workload(workload)
+    got = []
+    for R in (gpu, cpu):
+        ctx = R.RenderContext(w, h, alpha)
+        tex = [R.Texture.from_numpy(t) for t in tex_np]
+        trace.Replayer(REPLAY_LIB, R.path).run(ctx, arr, tex)
+        got.append(cases.digest(ctx))
+    return got
+
+
+def test_c3_full_size_matches_reference_4k(gpu, ref):
+    """BASELINE config 3 (affine variant) at full size — 3840x2160 RGBA, 50,000 atlas sprites — against the UNMODIFIED
+    reference build (about 20 s of one host core)."""
+    got = _full_size_vs_cpu(gpu, ref, "c3")
+    assert got[0] == got[1]
+
+
+def test_c4_full_size_matches_reference_rgb_canvas(gpu, ref):
+    """The milrenderer-shaped 1080p frame on a 3-channel canvas (mil:114 uses enable_alpha=False): identity-path
+    background, FillColor dim, gradients, DrawLine bodies, notes, hit effects — against the unmodified reference."""
+    got = _full_size_vs_cpu(gpu, ref, "c4")
+    assert got[0] == got[1]
