@@ -761,7 +761,8 @@ static void fill_texture_fields(NcrContext* c, NcrCmd* cmd, const void* ptr, uin
     if (c->sampling == 1) cmd->flags |= NCR_F_BILINEAR;
     else if ((tflags & NCR_F_TEX_ALPHA) && !(tflags & NCR_F_TEX_F64) && tw * th < 0x7fffffffL) {
         cmd->flags |= NCR_F_TEX_FAST;
-        if (cmd->op == NCR_OP_TEX || cmd->op == NCR_OP_TEX_SPLIT) cmd->flags |= NCR_F_FAST_AFFINE;
+        // the composite's hot path: DrawTexture, and DrawSplittedTexture on power-of-two textures (no division)
+        if (cmd->op == NCR_OP_TEX || (cmd->op == NCR_OP_TEX_SPLIT && is_pow2(tw) && is_pow2(th))) cmd->flags |= NCR_F_FAST_AFFINE;
     }
     cmd->tex_w = (int32_t)tw;
     cmd->tex_h = (int32_t)th;

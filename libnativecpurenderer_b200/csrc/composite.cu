@@ -21,6 +21,13 @@
 #include "ncr_cmd.h"
 #include "pixel_math.cuh"
 
+// Instruction-cache footprint matters more than call overhead here (ncu: a kernel that outgrows the I-cache stalls on
+// `no_inst`): f64 divisions and square roots only occur in the rarer ops, so they are calls, not ~40 inlined instructions each.
+__device__ __noinline__ double ncr_div(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __noinline__ double ncr_sqrt(double a) { return __dsqrt_rn(a); }
+#undef DIV
+#define DIV(a, b) ncr_div((a), (b))
+
 #define FULL 0xffffffffu
 #define NCR_LUT_COPIES 16
 #define NCR_COMPOSITE_THREADS 128
@@ -107,7 +114,7 @@ __device__ __noinline__ void sample_slow(const void* tex, uint32_t flags, int w,
 }
 
 // pointInPolygon, reference cpp:822-845 (even-odd rule; the divide is only evaluated on crossing edges).
-__device__ __forceinline__ bool point_in_poly(const double* __restrict__ pts, uint32_t n, double x, double y) {
+__device__ __noinline__ bool point_in_poly(const double* __restrict__ pts, uint32_t n, double x, double y) {
     bool res = false;
     double xj = __ldg(pts + 2 * (n - 1)), yj = __ldg(pts + 2 * (n - 1) + 1);
     for (uint32_t i = 0; i < n; ++i) {
@@ -272,18 +279,12 @@ __device__ __forceinline__ void tex_fast(const NcrCmd& c, const uint32_t op, con
     if (op == NCR_OP_TEX_SPLIT) {
         // cpp:812-813: u = (uStart + (uEnd - uStart) * u / tex->width) * tex->width
         const double uS = c.p[0], dU = c.p[1], vS = c.p[2], dV = c.p[3], fw = c.p[4], fh = c.p[5];
-        if (flags & NCR_F_SPLIT_POW2) {
-            // width and height are powers of two: x / 2^k and x * 2^-k are the same correctly rounded value
-            const double rw = c.p[6], rh = c.p[7];
-            FOR4 {
-                u[p] = MUL(ADD(uS, MUL(MUL(dU, u[p]), rw)), fw);
-                v[p] = MUL(ADD(vS, MUL(MUL(dV, v[p]), rh)), fh);
-            }
-        } else {
-            FOR4 {
-                u[p] = MUL(ADD(uS, DIV(MUL(dU, u[p]), fw)), fw);
-                v[p] = MUL(ADD(vS, DIV(MUL(dV, v[p]), fh)), fh);
-            }
+        // the hot path only takes power-of-two textures here (the recorder routes the others to the general path):
+        // x / 2^k and x * 2^-k are the same correctly rounded value
+        const double rw = c.p[6], rh = c.p[7];
+        FOR4 {
+            u[p] = MUL(ADD(uS, MUL(MUL(dU, u[p]), rw)), fw);
+            v[p] = MUL(ADD(vS, MUL(MUL(dV, v[p]), rh)), fh);
         }
     }
     // InterpolateColorFromBuffer, cpp:560-566: clamp u<0 -> 0, u >= w-1 -> w-2, then (i64) truncation.  Done after the
@@ -388,7 +389,7 @@ __device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A
             const double cx = c.x, cy = c.y, rad = c.sx;
             FOR4 if (__any_sync(FULL, in[p])) {
                 const double ddx = SUB(X[p], cx), ddy = SUB(Y[p], cy);
-                const double dist = __dsqrt_rn(ADD(MUL(ddx, ddx), MUL(ddy, ddy)));
+                const double dist = ncr_sqrt(ADD(MUL(ddx, ddx), MUL(ddy, ddy)));
                 in[p] = in[p] && !(dist > rad);
             }
         } else if (op == NCR_OP_POLY) {   // cpp:913
@@ -473,8 +474,7 @@ __device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A
             yi = max(yi, 0);
             tx[p] = in[p] ? __ldg(t32 + (yi * tw + xi)) : 0u;
         }
-        if (flags & NCR_F_CT_RGB_ONE) shade_rgba8<ALPHA, COUNT, true>(c, lut_base, tx, in, dr, dg, db, da, n_applied);
-        else shade_rgba8<ALPHA, COUNT, false>(c, lut_base, tx, in, dr, dg, db, da, n_applied);
+        shade_rgba8<ALPHA, COUNT, false>(c, lut_base, tx, in, dr, dg, db, da, n_applied);   // r * 1.0 is exact: one code copy
     } else {
         FOR4 if (in[p]) {
             double s[4];
