@@ -11,7 +11,7 @@ composited (ncr_bin_coarse -> ncr_bin_fine -> ncr_composite with the fused u8 im
              context's stream, L2 scrubbed (256 MB memset) before every step.  N ranks render independent
              frames (frame sharding, no collective): value = N*K / max-over-ranks(time).
   e2e        the same frames through the reference-facing C ABI from HOST buffers: the recorded stream is replayed
-             call by call (oracle/ncr_replay.cpp -> CreateRenderContext/Translate/.../DrawTexture/GetBufferAsUInt8
+             call by call (csrc/ncr_replay.cpp -> CreateRenderContext/Translate/.../DrawTexture/GetBufferAsUInt8
              of the product library), which includes the host state machine, the H2D copy of the command batch
              from pinned staging and the D2H readback of the RGBA8 frame; wall clock, T host threads with one
              context each (the reference API has no globals, so this is legal for it too).
@@ -179,7 +179,7 @@ def cpu_arm(workload: str, threads: int, sample_draws: int, steps: int, warmup: 
     w, h, alpha, tex_np, arr, draws, full = build_workload(workload, sample_draws)
     R = Renderer(lib)
     tex = [R.Texture.from_numpy(t) for t in tex_np]
-    rp = trace.Replayer(os.path.join(ROOT, "oracle", "libncr_replay.so"), lib)
+    rp = trace.Replayer(os.path.join(ROOT, "libnativecpurenderer_b200", "lib", "libncr_replay.so"), lib)
     frac = min(1.0, sample_draws / full)
     for _ in range(warmup):
         rp.run_threads(threads, w, h, alpha, arr, tex, repeats=1)
@@ -301,7 +301,7 @@ def run_product(args) -> None:
     clk = clocks.summary()
 
     # ---- e2e: host buffers in, host frame out, through the reference C ABI --------------------------------
-    rp = trace.Replayer(os.path.join(ROOT, "oracle", "libncr_replay.so"), R.path)   # the replayer is only a C caller
+    rp = trace.Replayer(os.path.join(ROOT, "libnativecpurenderer_b200", "lib", "libncr_replay.so"), R.path)   # the replayer is only a C caller
     T = args.e2e_threads or min(8, max(1, host_threads() // max(1, world)))
     e2e_frames_per_thread = max(2, min(K, args.e2e_frames))
     barrier()

@@ -89,6 +89,24 @@ def build_product(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+REPLAY_LIB = os.path.join(LIBDIR, "libncr_replay.so")
+
+
+def build_replayer(force: bool = False) -> str:
+    """Host-side trace replayer (csrc/ncr_replay.cpp): a plain C++ caller of the reference C ABI through dlopen, used by
+    bench.py's end-to-end measurement and by tests to drive any of the libraries without per-call FFI cost."""
+    os.makedirs(LIBDIR, exist_ok=True)
+    src = os.path.join(CSRC, "ncr_replay.cpp")
+    if not force and _newer(REPLAY_LIB, [src, os.path.join(CSRC, "ncr_trace.h")]):
+        return REPLAY_LIB
+    cmd = [os.environ.get("CXX", "g++"), "-shared", "-fPIC", "-O2", "-std=c++17", "-Wall", "-o", REPLAY_LIB, src, "-ldl", "-lpthread"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("replayer build failed")
+    return REPLAY_LIB
+
+
 def build_oracles() -> None:
     """CPU checkers under oracle/ (test infrastructure; building them is not using them)."""
     res = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "all"], capture_output=True, text=True)
@@ -99,6 +117,7 @@ def build_oracles() -> None:
 
 def main(argv: list[str]) -> int:
     build_product(force="--force" in argv, verbose="-v" in argv)
+    build_replayer(force="--force" in argv)
     if "--product" not in argv:
         build_oracles()
     print(LIB)

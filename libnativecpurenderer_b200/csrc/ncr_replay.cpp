@@ -1,4 +1,4 @@
-// TEST / MEASUREMENT INFRASTRUCTURE ONLY — not part of the product library.
+// Host-side trace replayer (built as lib/libncr_replay.so, separate from the product library).
 //
 // Trace replayer: dlopen()s any shared library exporting the reference C ABI (the unmodified reference
 // build in oracle/_ref, the C restatement libncr_oracle.so, or the product) and feeds it a recorded
@@ -15,7 +15,7 @@
 #include <thread>
 #include <vector>
 
-#include "../libnativecpurenderer_b200/csrc/ncr_trace.h"
+#include "ncr_trace.h"
 
 namespace {
 

@@ -3,7 +3,7 @@
 // A trace is a flat sequence of records { uint32 op; uint32 n; double args[n]; } — one record per call
 // of the reference C ABI (include/ncr_b200.h §1).  Texture arguments are slot numbers (stored as a
 // double) resolved against the texture table handed to the replayer.  Writers: trace.py.  Readers:
-// NcrSubmitTrace (api.cu, product) and oracle/ncr_replay.cpp (drives any library through dlsym).
+// NcrSubmitTrace (api.cu, product) and libnativecpurenderer_b200/csrc/ncr_replay.cpp (drives any library through dlsym).
 #pragma once
 #include <stdint.h>
 

@@ -5,7 +5,7 @@ pyb:51-300 method names) but appends binary records instead of calling a library
 replayed without per-call FFI cost by
 
 * ``NcrSubmitTrace`` (product, include/ncr_b200.h §2), or
-* ``oracle/ncr_replay.cpp`` (any library exporting the reference C ABI; measurement/tests only).
+* ``libnativecpurenderer_b200/csrc/ncr_replay.cpp`` (any library exporting the reference C ABI; measurement/tests only).
 
 Record layout: ``uint32 op, uint32 n, float64 args[n]`` (csrc/ncr_trace.h).  Texture arguments are
 slot numbers into the texture table given at replay time; use ``TexSlot`` in place of a ``Texture``.
@@ -134,7 +134,7 @@ def submit_trace(ctx, trace: np.ndarray, textures) -> int:
 
 
 class Replayer:
-    """ctypes face of oracle/libncr_replay.so bound to one target library (tests / bench only)."""
+    """ctypes face of lib/libncr_replay.so bound to one target library (tests / bench only)."""
 
     def __init__(self, replay_lib_path: str, target_lib_path: str):
         self.lib = ctypes.CDLL(replay_lib_path)

@@ -14,7 +14,7 @@ if ROOT not in sys.path:
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libNativeCPURenderer.so")
 PORT_LIB = os.path.join(ROOT, "oracle", "libncr_oracle.so")
-REPLAY_LIB = os.path.join(ROOT, "oracle", "libncr_replay.so")
+REPLAY_LIB = os.path.join(ROOT, "libnativecpurenderer_b200", "lib", "libncr_replay.so")
 
 
 def pytest_configure(config):
@@ -27,7 +27,8 @@ def _built():
     from libnativecpurenderer_b200 import build
 
     build.build_product()
-    if not (os.path.exists(PORT_LIB) and os.path.exists(REPLAY_LIB)):
+    build.build_replayer()
+    if not os.path.exists(PORT_LIB):
         build.build_oracles()
 
 

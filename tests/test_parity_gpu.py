@@ -63,7 +63,7 @@ def test_state_machine_is_bit_identical(gpu, port):
 
 
 def test_trace_replay_equals_direct_calls(gpu, image_rgba):
-    """NcrSubmitTrace (one FFI crossing) and oracle/ncr_replay (C calls) render what per-call ctypes renders."""
+    """NcrSubmitTrace (one FFI crossing) and csrc/ncr_replay (C calls) render what per-call ctypes renders."""
     from conftest import REPLAY_LIB
 
     tex_np = streams.make_c2_textures()
