@@ -382,3 +382,13 @@ def test_c4_full_size_matches_reference_rgb_canvas(gpu, ref):
     background, FillColor dim, gradients, DrawLine bodies, notes, hit effects — against the unmodified reference."""
     got = _full_size_vs_cpu(gpu, ref, "c4")
     assert got[0] == got[1]
+
+
+def test_fuzz_many_seeds_against_port(gpu, port, image_rgba):
+    """Sixty more seeded streams (five canvas shapes incl. 3-channel and ragged sizes, three flushes each), u8 + f64."""
+    bad = []
+    for seed in range(1000, 1060):
+        run = cases.make_random_case(seed, use_apply_pixel=(seed % 2 == 0))
+        if run(gpu, image_rgba) != run(port, image_rgba):
+            bad.append(seed)
+    assert not bad, f"seeds that differ from the C restatement: {bad}"
