@@ -45,6 +45,10 @@ WORKLOADS = {
                              "2% DrawLine; rotated/scaled, per-draw alpha), nearest sampling, seed 2"),
     "c3": (3840, 2160, True, "BASELINE config 3 (affine variant, SURVEY C3): 3840x2160 RGBA, 50,000 atlas sprites via "
                              "DrawSplittedTexture from a 2048^2 8x8-cell atlas, seed 3"),
+    "c2x": (1920, 1080, True, "BASELINE config 2 with the extensions it names (PRODUCT ONLY, parity unpinned): the C2 stream with bilinear "
+                             "sampling on half of the textured draws, N-gon fills instead of rects, and clip rects toggled every 500 draws"),
+    "c3p": (3840, 2160, True, "BASELINE config 3, perspective variant (PRODUCT ONLY, parity unpinned): 3840x2160 RGBA, 50,000 "
+                              "perspective-warped sprites from a 2048^2 atlas via NcrDrawTexturePerspective"),
     "bg": (1920, 1080, True, "low-overdraw end of the path: 1920x1080 RGBA, SetColor + full-screen DrawTexture (identity path) + FillColor "
                             "dim, u8 readback (3 commands per tile; the HBM-leaning regime)"),
     "c4": (1920, 1080, False, "BASELINE config 4 frame (SURVEY C4): 1920x1080 RGB milrenderer-shaped chart frame, ~1,500 notes, "
@@ -70,6 +74,14 @@ def build_workload(name: str, n_draws: int | None = None):
         tex_np = [streams.make_atlas()]
         full = 50000
         streams.stream_c3(rec, trace.TexSlot(0, 2048, 2048), n=n_draws or full)
+    elif name == "c2x":
+        tex_np = streams.make_c2_textures()
+        full = 20000
+        streams.stream_c2x(rec, [trace.TexSlot(k, t.shape[1], t.shape[0]) for k, t in enumerate(tex_np)], n=n_draws or full)
+    elif name == "c3p":
+        tex_np = [streams.make_atlas()]
+        full = 50000
+        streams.stream_c3p(rec, trace.TexSlot(0, 2048, 2048), n=n_draws or full)
     elif name == "bg":
         tex_np = [np.ascontiguousarray(np.resize(streams.make_noise_texture(256, 7), (h, w, 4)))]
         full = 2
@@ -199,6 +211,9 @@ def run_reference(args) -> None:
     threads = min(host_threads(), 64)
     _, _, _, _, _, _, full = build_workload(args.workload, 8)
     # one full C2 frame is ~16 s of one core; size the per-step sample so K+W steps end within ~2.5 minutes
+    if args.workload in ("c2x", "c3p"):
+        print(json.dumps({"impl": "reference", "unavailable": "the reference has no clip/bilinear/polygon/perspective entry points"}))
+        return
     per_frame_s = {"c1": 1.1, "c2": 16.0, "c3": 60.0, "c4": 3.0, "bg": 0.1}[args.workload]
     budget = 150.0 / max(1, args.steps + args.warmup)
     sample = int(max(min(full, 200), min(full, full * budget / per_frame_s)))
@@ -359,7 +374,7 @@ def run_product(args) -> None:
         "host_wall_s_value_region": wall_value,
     }
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload not in ("c2x", "c3p"):
         threads = min(host_threads(), 64)
         sample = {"c1": 1000, "c2": 20000, "c3": 12000, "c4": 1500, "bg": 2}[args.workload]
         fps, kind, text, _ = cpu_arm(args.workload, threads, sample, 1, 0)

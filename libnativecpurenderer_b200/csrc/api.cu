@@ -1191,8 +1191,42 @@ void NcrDrawTexturePerspective(RenderContext* ctx, Texture* tex_, const double i
     tex_dims(tex, &tw, &th);
     const void* ptr; uint32_t tflags; DevRef snap; const DevRef* keep = nullptr;
     if (!bind_texture(tex, &ptr, &tflags, &snap, &keep)) return;
-    // No forward map is available for a general projective inverse: cover the canvas (or the clip rect).
-    NcrCmd* cmd = begin_cmd(c, NCR_OP_TEX_PERSP, 0, c->w, 0, c->h);
+    // Pixel box: forward-map the source rectangle through the inverse of inv_h (a projective map keeps the rectangle's
+    // image inside the hull of its corners as long as the homogeneous w stays positive on it), pad, and fall back to the
+    // whole canvas whenever that cannot be trusted (singular / ill-conditioned matrix, w <= 0 at a corner, non-finite).
+    i64 bl = 0, br = c->w, bt = 0, bb = c->h;
+    {
+        const double* h = inv_h;
+        const double A0 = h[4] * h[8] - h[5] * h[7], A1 = h[2] * h[7] - h[1] * h[8], A2 = h[1] * h[5] - h[2] * h[4];
+        const double B0 = h[5] * h[6] - h[3] * h[8], B1 = h[0] * h[8] - h[2] * h[6], B2 = h[2] * h[3] - h[0] * h[5];
+        const double C0 = h[3] * h[7] - h[4] * h[6], C1 = h[1] * h[6] - h[0] * h[7], C2 = h[0] * h[4] - h[1] * h[3];
+        const double det = h[0] * A0 + h[1] * B0 + h[2] * C0;
+        bool ok = det != 0 && isfinite(det);
+        double minx = INFINITY, maxx = -INFINITY, miny = INFINITY, maxy = -INFINITY;
+        const double cxs[4] = {x, x + width, x, x + width}, cys[4] = {y, y, y + height, y + height};
+        const double tol = 1e-6 * (fabs(width) + fabs(height));
+        for (int k = 0; ok && k < 4; ++k) {
+            const double X = A0 * cxs[k] + A1 * cys[k] + A2, Y = B0 * cxs[k] + B1 * cys[k] + B2;
+            const double Wd = (C0 * cxs[k] + C1 * cys[k] + C2) / det;
+            const double px = X / det / Wd, py = Y / det / Wd;
+            if (!(Wd > 0) || !isfinite(px) || !isfinite(py) || fabs(px) > 1e7 || fabs(py) > 1e7) { ok = false; break; }
+            // trust the forward-mapped corner only if mapping it back through inv_h reproduces the source corner
+            const double bw = h[6] * px + h[7] * py + h[8];
+            const double bxs = (h[0] * px + h[1] * py + h[2]) / bw, bys = (h[3] * px + h[4] * py + h[5]) / bw;
+            if (!(bw > 0) || !(fabs(bxs - cxs[k]) <= tol) || !(fabs(bys - cys[k]) <= tol)) { ok = false; break; }
+            minx = std::min(minx, px); maxx = std::max(maxx, px);
+            miny = std::min(miny, py); maxy = std::max(maxy, py);
+        }
+        if (ok) {
+            const double pad = 2.0;
+            const double L = floor(minx - pad), R = ceil(maxx + pad) + 1, T = floor(miny - pad), B = ceil(maxy + pad) + 1;
+            bl = L <= 0 ? 0 : (L >= (double)c->w ? c->w : (i64)L);
+            br = R <= 0 ? 0 : (R >= (double)c->w ? c->w : (i64)R);
+            bt = T <= 0 ? 0 : (T >= (double)c->h ? c->h : (i64)T);
+            bb = B <= 0 ? 0 : (B >= (double)c->h ? c->h : (i64)B);
+        }
+    }
+    NcrCmd* cmd = begin_cmd(c, NCR_OP_TEX_PERSP, bl, br, bt, bb);
     if (!cmd) return;
     fill_texture_fields(c, cmd, ptr, tflags, *keep, tw, th);
     for (int k = 0; k < 6; ++k) cmd->inv[k] = inv_h[k];

@@ -48,6 +48,12 @@ struct Api {
     long (*GetBufferSize)(H) = nullptr;
     void* (*NcrAllocHost)(unsigned long long) = nullptr;   // optional (product): pinned readback destination
     void (*NcrFreeHost)(void*) = nullptr;
+    // optional: the additive extension entry points (include/ncr_b200.h section 2)
+    void (*NcrSetClipRect)(H, long, long, long, long) = nullptr;
+    void (*NcrClearClipRect)(H) = nullptr;
+    void (*NcrSetSampling)(H, int) = nullptr;
+    void (*NcrFillPolygon)(H, const double*, long, double, double, double, double) = nullptr;
+    void (*NcrDrawTexturePerspective)(H, H, const double*, double, double, double, double) = nullptr;
 };
 
 template <class F>
@@ -70,7 +76,7 @@ long run_trace(const Api& a, H ctx, const unsigned char* p, long bytes, H const*
         const double* v = (const double*)p;
         p += (size_t)rec.n * sizeof(double);
         H t = nullptr;
-        if (rec.op == NCR_T_DRAW_TEXTURE || rec.op == NCR_T_DRAW_SPLIT) {
+        if (rec.op == NCR_T_DRAW_TEXTURE || rec.op == NCR_T_DRAW_SPLIT || rec.op == NCR_T_DRAW_PERSP) {
             long slot = (long)v[0];
             if (slot < 0 || slot >= ntex) return -1;
             t = tex[slot];
@@ -102,7 +108,27 @@ long run_trace(const Api& a, H ctx, const unsigned char* p, long bytes, H const*
                 if (frame) a.GetBufferAsUInt8(ctx, frame);
                 if (presents) ++*presents;
                 break;
-            default: return -1;   // extension records are product-only (NcrSubmitTrace)
+            case NCR_T_CLIP_SET:
+                if (!a.NcrSetClipRect) return -1;
+                a.NcrSetClipRect(ctx, (long)v[0], (long)v[1], (long)v[2], (long)v[3]);
+                break;
+            case NCR_T_CLIP_CLEAR:
+                if (!a.NcrClearClipRect) return -1;
+                a.NcrClearClipRect(ctx);
+                break;
+            case NCR_T_SAMPLING:
+                if (!a.NcrSetSampling) return -1;
+                a.NcrSetSampling(ctx, (int)v[0]);
+                break;
+            case NCR_T_FILL_POLY:
+                if (!a.NcrFillPolygon || rec.n < 6 || (rec.n & 1)) return -1;
+                a.NcrFillPolygon(ctx, v + 4, (rec.n - 4) / 2, v[0], v[1], v[2], v[3]);
+                break;
+            case NCR_T_DRAW_PERSP:
+                if (!a.NcrDrawTexturePerspective || rec.n != 14) return -1;
+                a.NcrDrawTexturePerspective(ctx, t, v + 1, v[10], v[11], v[12], v[13]);
+                break;
+            default: return -1;   // unknown record, or an extension the target library does not export
         }
         ++n;
     }
@@ -135,6 +161,11 @@ void* ncr_replay_open(const char* path) {
     bind(dl, "ApplyPixel", a->ApplyPixel, false);
     bind(dl, "NcrAllocHost", a->NcrAllocHost, false);
     bind(dl, "NcrFreeHost", a->NcrFreeHost, false);
+    bind(dl, "NcrSetClipRect", a->NcrSetClipRect, false);
+    bind(dl, "NcrClearClipRect", a->NcrClearClipRect, false);
+    bind(dl, "NcrSetSampling", a->NcrSetSampling, false);
+    bind(dl, "NcrFillPolygon", a->NcrFillPolygon, false);
+    bind(dl, "NcrDrawTexturePerspective", a->NcrDrawTexturePerspective, false);
     if (!ok) {
         delete a;
         return nullptr;

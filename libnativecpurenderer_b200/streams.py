@@ -370,3 +370,75 @@ def stream_extensions(ctx, textures, seed: int, n: int = 60) -> None:
         ctx.restore_state()
     ctx.clear_clip_rect()
     ctx.set_sampling(0)
+
+
+def stream_c2x(ctx, textures, n: int = 20000, seed: int = 2) -> None:
+    """BASELINE config 2 as written, extensions included (product only): the C2 mix with bilinear sampling on half of the
+    textured draws, N-gon fills in place of rects, and a clip rect that changes every 500 draws."""
+    W, H = ctx.width, ctx.height
+    rng = random.Random(seed)
+    ctx.set_color(.1, .1, .1, 1)
+    for k in range(n):
+        if k % 500 == 0:
+            if (k // 500) % 3 == 2:
+                ctx.clear_clip_rect()
+            else:
+                ctx.set_clip_rect(int(rng.uniform(0, W * .3)), int(rng.uniform(0, H * .3)), int(W * .7), int(H * .7))
+        kind = rng.random()
+        ctx.save_state()
+        ctx.translate(rng.uniform(0, W), rng.uniform(0, H))
+        ctx.rotate(rng.uniform(0, TWO_PI))
+        s = rng.uniform(0.1, 0.6)
+        ctx.scale(s, s)
+        ctx.apply_color_transform(1, 1, 1, 1.0 if rng.random() < 0.2 else rng.uniform(0.1, 1.0))
+        if kind < 0.80:
+            tex = textures[rng.randrange(len(textures))]
+            ctx.set_sampling(1 if rng.random() < 0.5 else 0)
+            if kind < 0.60:
+                ctx.draw_texture(tex, -tex.width / 2, -tex.height / 2, tex.width, tex.height)
+            else:
+                u0, v0 = rng.uniform(0, .5), rng.uniform(0, .5)
+                ctx.draw_splitted_texture(tex, -tex.width / 2, -tex.height / 2, tex.width, tex.height,
+                                          u0, u0 + rng.uniform(.2, .5), v0, v0 + rng.uniform(.2, .5))
+        elif kind < 0.90:
+            m = rng.choice([3, 5, 6])
+            pts = [(120 * math.cos(TWO_PI * j / m) * rng.uniform(.6, 1), 120 * math.sin(TWO_PI * j / m) * rng.uniform(.6, 1))
+                   for j in range(m)]
+            ctx.fill_polygon(pts, rng.random(), rng.random(), rng.random(), rng.uniform(.2, 1))
+        elif kind < 0.95:
+            ctx.draw_vertical_grd(-120, -120, 240, 240, rng.random(), rng.random(), rng.random(), rng.uniform(0, .5),
+                                  rng.random(), rng.random(), rng.random(), rng.uniform(.5, 1))
+        elif kind < 0.98:
+            ctx.draw_circle(0, 0, rng.uniform(40, 160), rng.random(), rng.random(), rng.random(), rng.uniform(.2, 1))
+        else:
+            ctx.draw_line(-300, rng.uniform(-50, 50), 300, rng.uniform(-50, 50), rng.uniform(4, 30),
+                          rng.random(), rng.random(), rng.random(), rng.uniform(.3, 1))
+        ctx.restore_state()
+    ctx.clear_clip_rect()
+    ctx.set_sampling(0)
+
+
+def stream_c3p(ctx, atlas, n: int = 50000, seed: int = 3, cells: int = 8) -> None:
+    """BASELINE config 3, perspective variant (product only): n perspective-warped quads textured from the 2048^2 atlas.
+    The inverse homography maps canvas pixels into a 256x256 source square; like DrawTexture, the square is mapped onto the
+    whole texture, so every quad samples the full 16.8 MB atlas 8x minified (a texture-cache / L2 stress, as the config asks)."""
+    W, H = ctx.width, ctx.height
+    rng = random.Random(seed)
+    ctx.set_color(0, 0, 0, 1)
+    cell = atlas.width / cells
+    for _ in range(n):
+        cx, cy = rng.randrange(cells), rng.randrange(cells)
+        tx_, ty_ = rng.uniform(0, W), rng.uniform(0, H)
+        ang = rng.uniform(0, TWO_PI)
+        k_ = 1.0 / rng.uniform(0.05, 0.5)
+        c_, s_ = math.cos(ang) * k_, math.sin(ang) * k_
+        ox, oy = (cx + .5) * cell, (cy + .5) * cell   # the source square's centre
+        g, hh = rng.uniform(-2e-4, 2e-4), rng.uniform(-2e-4, 2e-4)   # mild projective term
+        w0 = 1.0 - g * tx_ - hh * ty_
+        hinv = (c_ + ox * g, s_ + ox * hh, -(c_ * tx_ + s_ * ty_) + ox * w0,
+                -s_ + oy * g, c_ + oy * hh, (s_ * tx_ - c_ * ty_) + oy * w0,
+                g, hh, w0)
+        ctx.save_state()
+        ctx.apply_color_transform(1, 1, 1, rng.uniform(0.2, 1.0))
+        ctx.draw_texture_perspective(atlas, hinv, cx * cell, cy * cell, cell, cell)
+        ctx.restore_state()

@@ -392,3 +392,16 @@ def test_fuzz_many_seeds_against_port(gpu, port, image_rgba):
         if run(gpu, image_rgba) != run(port, image_rgba):
             bad.append(seed)
     assert not bad, f"seeds that differ from the C restatement: {bad}"
+
+
+def test_perspective_pixel_box_is_conservative(gpu, port):
+    """The recorder bounds a perspective quad by the forward-mapped source rectangle; the restatement scans the whole canvas.
+    Same pixels must come out (extension: parity unpinned against the reference, pinned between the two implementations)."""
+    atlas_np = streams.make_atlas(cells=4, cell=32)
+    got = []
+    for R in (gpu, port):
+        ctx = R.RenderContext(384, 216, True)
+        atlas = R.Texture.from_numpy(atlas_np)
+        streams.stream_c3p(ctx, atlas, n=400, cells=4)
+        got.append(cases.digest(ctx))
+    assert got[0] == got[1]
