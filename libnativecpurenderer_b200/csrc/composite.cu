@@ -29,8 +29,14 @@ __device__ __noinline__ double ncr_sqrt(double a) { return __dsqrt_rn(a); }
 #define DIV(a, b) ncr_div((a), (b))
 
 #define FULL 0xffffffffu
-#define NCR_LUT_COPIES 16
-#define NCR_COMPOSITE_THREADS 128
+// u8 -> k/255.0 table: one private copy per lane (32 copies, entries 256 B apart), so a lookup is conflict-free and its
+// shared address is a single byte permute of (texel, lane*8): byte 1 <- texel byte, byte 0 <- lane*8.
+#define NCR_LUT_COPIES 32
+#define NCR_LUT_BYTES (256 * NCR_LUT_COPIES * 8)
+#define NCR_SMEM_BYTES (NCR_LUT_BYTES + (NCR_COMPOSITE_THREADS / 32) * 2 * (int)sizeof(NcrCmd))
+#ifndef NCR_COMPOSITE_THREADS
+#define NCR_COMPOSITE_THREADS 384
+#endif
 // Pixel slots per lane: NCR_NX columns x 2 rows of 8x4 blocks.  NX=2: a warp owns a 16x8 half-tile (4 px per lane);
 // NX=1: an 8x8 quarter-tile (2 px per lane: half the register state, twice the warps per tile).
 #ifndef NCR_NX
@@ -43,10 +49,13 @@ __device__ __noinline__ double ncr_sqrt(double a) { return __dsqrt_rn(a); }
 #define SX(p) ((p) % NCR_NX)
 #define SY(p) ((p) / NCR_NX)
 #ifndef NCR_COMPOSITE_MIN_CTAS
-#define NCR_COMPOSITE_MIN_CTAS 3
+#define NCR_COMPOSITE_MIN_CTAS 1   // one persistent 12-warp CTA per SM: one decode table per SM, the rest of the 256 KB stays L1
 #endif
 
 namespace {
+
+// Dynamic shared memory: [0, 64 KB) the decode table, then the per-warp command slots.
+extern __shared__ __align__(256) unsigned char ncr_smem[];
 
 // InterpolateColorFromBuffer's clamp, reference cpp:560-563, then truncation (cpp:566).
 __device__ __forceinline__ void clamp_uv(double& u, double& v, int w, int h) {
@@ -62,15 +71,15 @@ __device__ __forceinline__ void fetch_any(const void* tex, uint32_t flags, const
     if (!(flags & NCR_F_TEX_F64)) {
         if (flags & NCR_F_TEX_ALPHA) {
             const uint32_t t = __ldg((const uint32_t*)tex + idx);
-            r = lut[((t & 255u) << 4) | l16];
-            g = lut[(((t >> 8) & 255u) << 4) | l16];
-            b = lut[(((t >> 16) & 255u) << 4) | l16];
-            a = lut[((t >> 24) << 4) | l16];
+            r = lut[((t & 255u) * NCR_LUT_COPIES) | l16];
+            g = lut[(((t >> 8) & 255u) * NCR_LUT_COPIES) | l16];
+            b = lut[(((t >> 16) & 255u) * NCR_LUT_COPIES) | l16];
+            a = lut[((t >> 24) * NCR_LUT_COPIES) | l16];
         } else {
             const unsigned char* q = (const unsigned char*)tex + idx * 3;
-            r = lut[((uint32_t)__ldg(q) << 4) | l16];
-            g = lut[((uint32_t)__ldg(q + 1) << 4) | l16];
-            b = lut[((uint32_t)__ldg(q + 2) << 4) | l16];
+            r = lut[((uint32_t)__ldg(q) * NCR_LUT_COPIES) | l16];
+            g = lut[((uint32_t)__ldg(q + 1) * NCR_LUT_COPIES) | l16];
+            b = lut[((uint32_t)__ldg(q + 2) * NCR_LUT_COPIES) | l16];
             a = NCR_RGB_TEXTURE_ALPHA;
         }
     } else {
@@ -134,19 +143,27 @@ __device__ __noinline__ bool point_in_poly(const double* __restrict__ pts, uint3
 //     if (a != 1) c = dst*(1 - a) + c*a;   dst.rgb = c;   dst.a = a (canvas with alpha)
 // Lanes with a == 1 (plain store, cpp:533 skips the blend) are NOT handled here: the caller collects them in `opaque`
 // and applies store_opaque() under one warp-uniform branch, because they are rare.
+__device__ __forceinline__ void padd(double& d, double x, double y, bool p) {
+    const double n = ADD(x, y);
+    d = p ? n : d;
+}
+
+// a == 1.0 on the integer pipe (the FP64 pipe is the contended one): 1.0 has a single encoding, and no NaN equals it.
+__device__ __forceinline__ bool is_one(double a) {
+    return __double2hiint(a) == 0x3ff00000 && __double2loint(a) == 0;
+}
+
 template <bool ALPHA>
 __device__ __forceinline__ bool blend(double& dr, double& dg, double& db, double& da, double r, double g, double b, double a,
                                       bool in) {
-    const bool blended = in && (a != 1.0);   // true for NaN, as in C
+    const bool ne = !is_one(a);   // a != 1.0: true for NaN, as in C
+    const bool blended = in && ne;
     const double om = SUB(1.0, a);
-    const double nr = ADD(MUL(dr, om), MUL(r, a));
-    const double ng = ADD(MUL(dg, om), MUL(g, a));
-    const double nb = ADD(MUL(db, om), MUL(b, a));
-    dr = blended ? nr : dr;
-    dg = blended ? ng : dg;
-    db = blended ? nb : db;
+    padd(dr, MUL(dr, om), MUL(r, a), blended);
+    padd(dg, MUL(dg, om), MUL(g, a), blended);
+    padd(db, MUL(db, om), MUL(b, a), blended);
     if (ALPHA) da = in ? a : da;   // source alpha replaces destination alpha (cpp:544)
-    return in && !(a != 1.0);
+    return in && !ne;
 }
 
 __device__ __forceinline__ void store_opaque(double& dr, double& dg, double& db, double r, double g, double b, bool opaque) {
@@ -158,22 +175,19 @@ __device__ __forceinline__ void store_opaque(double& dr, double& dg, double& db,
 // Constant-colour blend (cpp:533-546 with the colour-only subexpressions formed on the host): dst = dst*om + q.
 __device__ __forceinline__ void blend_const(double& dr, double& dg, double& db, double om, double q0, double q1, double q2,
                                             bool in) {
-    const double nr = ADD(MUL(dr, om), q0), ng = ADD(MUL(dg, om), q1), nb = ADD(MUL(db, om), q2);
-    dr = in ? nr : dr;
-    dg = in ? ng : dg;
-    db = in ? nb : db;
+    padd(dr, MUL(dr, om), q0, in);
+    padd(dg, MUL(dg, om), q1, in);
+    padd(db, MUL(db, om), q2, in);
 }
 
 __device__ __forceinline__ void store_pred(double& d, double v, bool in) { d = in ? v : d; }
 
-// u8 -> k/255.0 through the replicated table: byte k of the packed texel, copy (lane & 15).  `base` is the shared-space
-// byte address of this lane's copy of entry 0; entries are 128 B apart.
+// u8 -> k/255.0 through the replicated table: byte K of the packed texel, this lane's copy.  `lane8` = lane * 8 (< 256);
+// the byte offset of entry k, copy lane, is (k << 8) | lane8 — one PRMT — and the table base folds into the LDS immediate.
 template <int K>
-__device__ __forceinline__ double lut_byte(uint32_t base, uint32_t texel) {
-    const uint32_t k = __byte_perm(texel, 0, 0x4440 + K);
-    double v;
-    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + k * 128u));
-    return v;
+__device__ __forceinline__ double lut_byte(uint32_t lane8, uint32_t texel) {
+    const uint32_t off = __byte_perm(texel, lane8, 0x6504 + (K << 4));
+    return *(const double*)((const char*)ncr_smem + off);
 }
 
 #define FOR4 _Pragma("unroll") for (int p = 0; p < NCR_P; ++p)
@@ -290,15 +304,14 @@ __device__ __forceinline__ void tex_fast(const NcrCmd& c, const uint32_t op, con
     // InterpolateColorFromBuffer, cpp:560-566: clamp u<0 -> 0, u >= w-1 -> w-2, then (i64) truncation.  Done after the
     // truncation here, which is the same function: trunc(u) <= 0 iff u < 1, and because w-1 is an integer,
     // u >= w-1 iff trunc(u) >= w-1 (cvt.rzi saturates, so huge u stays >= w-1).
-    const int tw = c.tex_w, th = c.tex_h;
+    const int tw = c.tex_w, tw2 = tw - 2, th2 = c.tex_h - 2;
     const uint32_t* t32 = (const uint32_t*)c.tex;
     uint32_t tx[NCR_P];
     FOR4 {
-        int xi = __double2int_rz(u[p]), yi = __double2int_rz(v[p]);
-        xi = xi >= tw - 1 ? tw - 2 : xi;
-        yi = yi >= th - 1 ? th - 2 : yi;
-        xi = max(xi, 0);   // also keeps 1-texel-wide textures in bounds (the reference reads out of bounds there)
-        yi = max(yi, 0);
+        // x >= w-1 ? w-2 : x is min(x, w-2) on integers; max(.., 0) also keeps 1-texel-wide textures in bounds (the
+        // reference reads out of bounds there).  min + relu is one VIMNMX.
+        const int xi = __vimin_s32_relu(__double2int_rz(u[p]), tw2);
+        const int yi = __vimin_s32_relu(__double2int_rz(v[p]), th2);
         tx[p] = in[p] ? __ldg(t32 + (yi * tw + xi)) : 0u;
     }
     if (flags & NCR_F_CT_RGB_ONE) shade_rgba8<ALPHA, COUNT, true>(c, lut_base, tx, in, dr, dg, db, da, n_applied);
@@ -307,20 +320,27 @@ __device__ __forceinline__ void tex_fast(const NcrCmd& c, const uint32_t op, con
 
 // One command applied to the warp's 128 pixels.  `c` lives in shared memory (warp-uniform reads: one wavefront each).
 template <bool ALPHA, bool COUNT>
-__device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A, const Slots& S, const double* lut /* + lane&15 */, uint32_t lut_base,
+__device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A, const Slots& S, const bool (&valid)[NCR_P], const bool cover,
+                                          const double* lut, uint32_t lut_base /* lane * 8 */,
                                           double (&dr)[NCR_P], double (&dg)[NCR_P], double (&db)[NCR_P], double (&da)[NCR_P],
                                           unsigned long long& n_applied) {
     const uint32_t op = c.op, flags = c.flags;
     // pixel-box membership: the reference's loop bounds (boxes are clamped to the canvas on the host, so a pixel slot
     // outside the canvas is never inside a box).  (unsigned)(v - lo) < (unsigned)(hi - lo)  <=>  lo <= v < hi.
-    const unsigned wx = (unsigned)(c.r - c.l), wy = (unsigned)(c.b - c.t);
-    bool inx[NCR_NX], iny[NCR_NY];
-#pragma unroll
-    for (int k = 0; k < NCR_NX; ++k) inx[k] = (unsigned)(S.xs[k] - c.l) < wx;
-#pragma unroll
-    for (int k = 0; k < NCR_NY; ++k) iny[k] = (unsigned)(S.ys[k] - c.t) < wy;
+    // `cover` (warp-uniform, from the list walk): the box contains every canvas pixel of this region, so membership is
+    // just "the slot is on the canvas".
     bool in[NCR_P];
-    FOR4 in[p] = inx[SX(p)] && iny[SY(p)];
+    if (cover) {
+        FOR4 in[p] = valid[p];
+    } else {
+        const unsigned wx = (unsigned)(c.r - c.l), wy = (unsigned)(c.b - c.t);
+        bool inx[NCR_NX], iny[NCR_NY];
+#pragma unroll
+        for (int k = 0; k < NCR_NX; ++k) inx[k] = (unsigned)(S.xs[k] - c.l) < wx;
+#pragma unroll
+        for (int k = 0; k < NCR_NY; ++k) iny[k] = (unsigned)(S.ys[k] - c.t) < wy;
+        FOR4 in[p] = inx[SX(p)] && iny[SY(p)];
+    }
 
     if (flags & NCR_F_FAST_AFFINE) {   // DrawTexture / DrawSplittedTexture on RGBA8, nearest: the hot case, tested first
         tex_fast<ALPHA, COUNT>(c, op, flags, S, lut, lut_base, in, dr, dg, db, da, n_applied);
@@ -467,18 +487,15 @@ __device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A
         const uint32_t* t32 = (const uint32_t*)c.tex;
         uint32_t tx[NCR_P];
         FOR4 {
-            int xi = __double2int_rz(u[p]), yi = __double2int_rz(v[p]);
-            xi = xi >= tw - 1 ? tw - 2 : xi;
-            yi = yi >= th - 1 ? th - 2 : yi;
-            xi = max(xi, 0);
-            yi = max(yi, 0);
+            const int xi = __vimin_s32_relu(__double2int_rz(u[p]), tw - 2);
+            const int yi = __vimin_s32_relu(__double2int_rz(v[p]), th - 2);
             tx[p] = in[p] ? __ldg(t32 + (yi * tw + xi)) : 0u;
         }
         shade_rgba8<ALPHA, COUNT, false>(c, lut_base, tx, in, dr, dg, db, da, n_applied);   // r * 1.0 is exact: one code copy
     } else {
         FOR4 if (in[p]) {
             double s[4];
-            sample_slow(c.tex, flags, tw, th, lut - (threadIdx.x & 15), threadIdx.x & 15, u[p], v[p], s);
+            sample_slow(c.tex, flags, tw, th, lut, threadIdx.x & 31, u[p], v[p], s);
             const double r = MUL(s[0], c.ct[0]), g = MUL(s[1], c.ct[1]), b = MUL(s[2], c.ct[2]), a = MUL(s[3], c.ct[3]);
             const bool opq = blend<ALPHA>(dr[p], dg[p], db[p], da[p], r, g, b, a, true);
             store_opaque(dr[p], dg[p], db[p], r, g, b, opq);
@@ -488,19 +505,23 @@ __device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A
 }
 
 template <bool ALPHA, bool COUNT>
+#ifdef NCR_MAXNREG
+__global__ void __maxnreg__(NCR_MAXNREG) ncr_composite(NcrFlushArgs A) {
+#else
 __global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, NCR_COMPOSITE_MIN_CTAS) ncr_composite(NcrFlushArgs A) {
-    // u8 / 255.0 (CreateTextureUInt8, cpp:350), IEEE division on both sides.  16 copies, copy c of entry k at
-    // [k*16 + c]: a lane only ever reads copy (lane & 15), so the 64-bit lookups of a half-warp never collide on a bank.
-    __shared__ double s_lut[256 * NCR_LUT_COPIES];
+#endif
+    // u8 / 255.0 (CreateTextureUInt8, cpp:350), IEEE division on both sides.  32 copies, copy c of entry k at [k*32 + c]:
+    // a lane only ever reads its own copy, so lookups never collide on a bank.
+    double* s_lut = (double*)ncr_smem;
     // Per-warp double-buffered command slot: the next command of the list is fetched while the current one is applied.
-    __shared__ NcrCmd s_cmd[NCR_COMPOSITE_THREADS / 32][2];
+    NcrCmd (*s_cmd)[2] = (NcrCmd (*)[2])(ncr_smem + NCR_LUT_BYTES);
     for (int e = threadIdx.x; e < 256 * NCR_LUT_COPIES; e += NCR_COMPOSITE_THREADS)
-        s_lut[e] = DIV((double)(e >> 4), 255.0);
+        s_lut[e] = DIV((double)(e / NCR_LUT_COPIES), 255.0);
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double* lut = s_lut + (lane & 15);
-    const uint32_t lut_base = (uint32_t)__cvta_generic_to_shared(lut);
+    const double* lut = s_lut;
+    const uint32_t lut_base = (uint32_t)lane * 8u;
     const int lx = lane & 7, ly = lane >> 3;
     const int n_tiles = A.d.tiles_x * A.d.tiles_y;
     const int n_tasks = n_tiles * NCR_TASKS_PER_TILE;
@@ -547,28 +568,34 @@ __global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, NCR_COMPOSITE_MIN_CTAS)
 
         // Walk the tile's list in submission order.  32 entries at a time: each lane tests one command's box against
         // this half-tile, the ballot is the set of commands to apply.
-        uint32_t k0 = 0, pending = 0, mine = 0;
+        uint32_t k0 = 0, pending = 0, covers = 0, mine = 0;
+        bool nxt_cover = false;
+        const int xe = min(x0 + NCR_RW, W), ye = min(y0 + 8, H);   // the region, clipped to the canvas
         auto next_cmd = [&]() -> int {   // warp-uniform: index of the next command touching this half, or -1
             while (pending == 0) {
                 if (k0 >= lcount) return -1;
-                bool hit = false;
+                bool hit = false, cov = false;
                 if (k0 + lane < lcount) {
                     mine = __ldg(&A.fine_list[loff + k0 + lane]);
                     const int4 box = __ldg((const int4*)&A.boxes[mine]);   // l, r, t, b
                     hit = box.z < y0 + 8 && box.w > y0 && box.x < x0 + NCR_RW && box.y > x0;
+                    cov = box.x <= x0 && box.y >= xe && box.z <= y0 && box.w >= ye;
                     if (hit) hit = !quad_misses_region(A.cmds + mine, max(x0, box.x), min(x0 + NCR_RW, box.y) - 1,
                                                        max(y0, box.z), min(y0 + 8, box.w) - 1);
                 }
                 pending = __ballot_sync(FULL, hit);
+                covers = __ballot_sync(FULL, cov);
                 k0 += 32;
             }
             const int kk = __ffs(pending) - 1;
             pending &= pending - 1;
+            nxt_cover = (covers >> kk) & 1u;
             return (int)__shfl_sync(FULL, mine, kk);
         };
 
         int slot = 0;
         int cur = next_cmd();
+        bool cur_cover = nxt_cover;
         if (cur >= 0) {
             if (lane < WORDS) ((uint4*)&s_cmd[warp][0])[lane] = __ldg((const uint4*)(A.cmds + cur) + lane);
             __syncwarp();
@@ -577,7 +604,8 @@ __global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, NCR_COMPOSITE_MIN_CTAS)
             const int nxt = next_cmd();
             uint4 pre = make_uint4(0, 0, 0, 0);
             if (nxt >= 0 && lane < WORDS) pre = __ldg((const uint4*)(A.cmds + nxt) + lane);   // in flight during apply_cmd
-            apply_cmd<ALPHA, COUNT>(s_cmd[warp][slot], A, S, lut, lut_base, dr, dg, db, da, n_applied);
+            apply_cmd<ALPHA, COUNT>(s_cmd[warp][slot], A, S, valid, cur_cover, lut, lut_base, dr, dg, db, da, n_applied);
+            cur_cover = nxt_cover;
             if (nxt >= 0 && lane < WORDS) ((uint4*)&s_cmd[warp][slot ^ 1])[lane] = pre;
             __syncwarp();
             slot ^= 1;
@@ -620,10 +648,11 @@ int g_grid[4] = {0, 0, 0, 0};
 template <bool ALPHA, bool COUNT>
 void launch(const NcrFlushArgs& A, cudaStream_t s, int slot) {
     if (g_grid[slot] == 0) {
-        int dev = 0, sms = 148, per_sm = 4;
+        int dev = 0, sms = 148, per_sm = 1;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ncr_composite<ALPHA, COUNT>, NCR_COMPOSITE_THREADS, 0);
+        cudaFuncSetAttribute(ncr_composite<ALPHA, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, NCR_SMEM_BYTES);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ncr_composite<ALPHA, COUNT>, NCR_COMPOSITE_THREADS, NCR_SMEM_BYTES);
         g_grid[slot] = sms * (per_sm > 0 ? per_sm : 1);   // persistent: every resident CTA slot, one wave
     }
     const int n_tasks = A.d.tiles_x * A.d.tiles_y * NCR_TASKS_PER_TILE;
@@ -631,7 +660,7 @@ void launch(const NcrFlushArgs& A, cudaStream_t s, int slot) {
     int grid = g_grid[slot];
     if (grid * warps > n_tasks) grid = (n_tasks + warps - 1) / warps;
     if (grid < 1) grid = 1;
-    ncr_composite<ALPHA, COUNT><<<grid, NCR_COMPOSITE_THREADS, 0, s>>>(A);
+    ncr_composite<ALPHA, COUNT><<<grid, NCR_COMPOSITE_THREADS, NCR_SMEM_BYTES, s>>>(A);
 }
 
 }   // namespace
