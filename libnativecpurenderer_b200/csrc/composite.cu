@@ -148,15 +148,10 @@ __device__ __forceinline__ void padd(double& d, double x, double y, bool p) {
     d = p ? n : d;
 }
 
-// a == 1.0 on the integer pipe (the FP64 pipe is the contended one): 1.0 has a single encoding, and no NaN equals it.
-__device__ __forceinline__ bool is_one(double a) {
-    return __double2hiint(a) == 0x3ff00000 && __double2loint(a) == 0;
-}
-
 template <bool ALPHA>
 __device__ __forceinline__ bool blend(double& dr, double& dg, double& db, double& da, double r, double g, double b, double a,
                                       bool in) {
-    const bool ne = !is_one(a);   // a != 1.0: true for NaN, as in C
+    const bool ne = (a != 1.0);   // true for NaN, as in C
     const bool blended = in && ne;
     const double om = SUB(1.0, a);
     padd(dr, MUL(dr, om), MUL(r, a), blended);
@@ -320,27 +315,21 @@ __device__ __forceinline__ void tex_fast(const NcrCmd& c, const uint32_t op, con
 
 // One command applied to the warp's 128 pixels.  `c` lives in shared memory (warp-uniform reads: one wavefront each).
 template <bool ALPHA, bool COUNT>
-__device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A, const Slots& S, const bool (&valid)[NCR_P], const bool cover,
+__device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A, const Slots& S,
                                           const double* lut, uint32_t lut_base /* lane * 8 */,
                                           double (&dr)[NCR_P], double (&dg)[NCR_P], double (&db)[NCR_P], double (&da)[NCR_P],
                                           unsigned long long& n_applied) {
     const uint32_t op = c.op, flags = c.flags;
     // pixel-box membership: the reference's loop bounds (boxes are clamped to the canvas on the host, so a pixel slot
     // outside the canvas is never inside a box).  (unsigned)(v - lo) < (unsigned)(hi - lo)  <=>  lo <= v < hi.
-    // `cover` (warp-uniform, from the list walk): the box contains every canvas pixel of this region, so membership is
-    // just "the slot is on the canvas".
+    const unsigned wx = (unsigned)(c.r - c.l), wy = (unsigned)(c.b - c.t);
+    bool inx[NCR_NX], iny[NCR_NY];
+#pragma unroll
+    for (int k = 0; k < NCR_NX; ++k) inx[k] = (unsigned)(S.xs[k] - c.l) < wx;
+#pragma unroll
+    for (int k = 0; k < NCR_NY; ++k) iny[k] = (unsigned)(S.ys[k] - c.t) < wy;
     bool in[NCR_P];
-    if (cover) {
-        FOR4 in[p] = valid[p];
-    } else {
-        const unsigned wx = (unsigned)(c.r - c.l), wy = (unsigned)(c.b - c.t);
-        bool inx[NCR_NX], iny[NCR_NY];
-#pragma unroll
-        for (int k = 0; k < NCR_NX; ++k) inx[k] = (unsigned)(S.xs[k] - c.l) < wx;
-#pragma unroll
-        for (int k = 0; k < NCR_NY; ++k) iny[k] = (unsigned)(S.ys[k] - c.t) < wy;
-        FOR4 in[p] = inx[SX(p)] && iny[SY(p)];
-    }
+    FOR4 in[p] = inx[SX(p)] && iny[SY(p)];
 
     if (flags & NCR_F_FAST_AFFINE) {   // DrawTexture / DrawSplittedTexture on RGBA8, nearest: the hot case, tested first
         tex_fast<ALPHA, COUNT>(c, op, flags, S, lut, lut_base, in, dr, dg, db, da, n_applied);
@@ -495,7 +484,7 @@ __device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A
     } else {
         FOR4 if (in[p]) {
             double s[4];
-            sample_slow(c.tex, flags, tw, th, lut, threadIdx.x & 31, u[p], v[p], s);
+            sample_slow(c.tex, flags, tw, th, lut, threadIdx.x & (NCR_LUT_COPIES - 1), u[p], v[p], s);
             const double r = MUL(s[0], c.ct[0]), g = MUL(s[1], c.ct[1]), b = MUL(s[2], c.ct[2]), a = MUL(s[3], c.ct[3]);
             const bool opq = blend<ALPHA>(dr[p], dg[p], db[p], da[p], r, g, b, a, true);
             store_opaque(dr[p], dg[p], db[p], r, g, b, opq);
@@ -568,34 +557,28 @@ __global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, NCR_COMPOSITE_MIN_CTAS)
 
         // Walk the tile's list in submission order.  32 entries at a time: each lane tests one command's box against
         // this half-tile, the ballot is the set of commands to apply.
-        uint32_t k0 = 0, pending = 0, covers = 0, mine = 0;
-        bool nxt_cover = false;
-        const int xe = min(x0 + NCR_RW, W), ye = min(y0 + 8, H);   // the region, clipped to the canvas
+        uint32_t k0 = 0, pending = 0, mine = 0;
         auto next_cmd = [&]() -> int {   // warp-uniform: index of the next command touching this half, or -1
             while (pending == 0) {
                 if (k0 >= lcount) return -1;
-                bool hit = false, cov = false;
+                bool hit = false;
                 if (k0 + lane < lcount) {
                     mine = __ldg(&A.fine_list[loff + k0 + lane]);
                     const int4 box = __ldg((const int4*)&A.boxes[mine]);   // l, r, t, b
                     hit = box.z < y0 + 8 && box.w > y0 && box.x < x0 + NCR_RW && box.y > x0;
-                    cov = box.x <= x0 && box.y >= xe && box.z <= y0 && box.w >= ye;
                     if (hit) hit = !quad_misses_region(A.cmds + mine, max(x0, box.x), min(x0 + NCR_RW, box.y) - 1,
                                                        max(y0, box.z), min(y0 + 8, box.w) - 1);
                 }
                 pending = __ballot_sync(FULL, hit);
-                covers = __ballot_sync(FULL, cov);
                 k0 += 32;
             }
             const int kk = __ffs(pending) - 1;
             pending &= pending - 1;
-            nxt_cover = (covers >> kk) & 1u;
             return (int)__shfl_sync(FULL, mine, kk);
         };
 
         int slot = 0;
         int cur = next_cmd();
-        bool cur_cover = nxt_cover;
         if (cur >= 0) {
             if (lane < WORDS) ((uint4*)&s_cmd[warp][0])[lane] = __ldg((const uint4*)(A.cmds + cur) + lane);
             __syncwarp();
@@ -604,8 +587,7 @@ __global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, NCR_COMPOSITE_MIN_CTAS)
             const int nxt = next_cmd();
             uint4 pre = make_uint4(0, 0, 0, 0);
             if (nxt >= 0 && lane < WORDS) pre = __ldg((const uint4*)(A.cmds + nxt) + lane);   // in flight during apply_cmd
-            apply_cmd<ALPHA, COUNT>(s_cmd[warp][slot], A, S, valid, cur_cover, lut, lut_base, dr, dg, db, da, n_applied);
-            cur_cover = nxt_cover;
+            apply_cmd<ALPHA, COUNT>(s_cmd[warp][slot], A, S, lut, lut_base, dr, dg, db, da, n_applied);
             if (nxt >= 0 && lane < WORDS) ((uint4*)&s_cmd[warp][slot ^ 1])[lane] = pre;
             __syncwarp();
             slot ^= 1;

@@ -1,6 +1,6 @@
-# development helper: GPU tests + quick A/B timing of the main build and any variants under lib/variants/
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+# development helper: GPU tests (unless SKIP_TESTS=1) + quick A/B timing of the main build and any variants under lib/variants/
+[ -n "$SKIP_TESTS" ] || python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 for v in main $(ls libnativecpurenderer_b200/lib/variants 2>/dev/null); do
   if [ $v = main ]; then unset NCR_LIBRARY; else export NCR_LIBRARY=$PWD/libnativecpurenderer_b200/lib/variants/$v/libNativeCPURenderer.so; fi
-  for w in ${WORKLOADS:-c2 c4}; do python bench.py --steps 30 --warmup 3 --workload $w --no-cpu-baseline --e2e-frames 4 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$v', d['metric'], round(d['value'],1), 'fps | e2e', round(d['e2e']['value'],1), '| ms', {k:round(x,3) for k,x in d['kernel_ms'].items()})"; done
+  for w in ${WORKLOADS:-c2 c4}; do python bench.py --steps ${STEPS:-30} --warmup 3 --workload $w --no-cpu-baseline --e2e-frames ${E2E:-4} 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$v', d['metric'], round(d['value'],1), 'fps | e2e', round(d['e2e']['value'],1), '| ms', {k:round(x,3) for k,x in d['kernel_ms'].items()})"; done
 done
