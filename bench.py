@@ -317,6 +317,9 @@ def run_product(args) -> None:
 
     # ---- e2e: host buffers in, host frame out, through the reference C ABI --------------------------------
     rp = trace.Replayer(os.path.join(ROOT, "libnativecpurenderer_b200", "lib", "libncr_replay.so"), R.path)   # the replayer is only a C caller
+    if args.present == "yuv420p":
+        rp.set_present("yuv420p")   # video present path: planes come back instead of the RGB(A)8 image
+    d2h_bytes = w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2) if args.present == "yuv420p" else frame_bytes
     T = args.e2e_threads or min(8, max(1, host_threads() // max(1, world)))
     e2e_frames_per_thread = max(2, min(K, args.e2e_frames))
     barrier()
@@ -352,10 +355,11 @@ def run_product(args) -> None:
                    "tile_list_entries": int(fine_entries), "blended_pixel_ops_per_frame": int(blended),
                    "parallelism": f"frame-sharded replicas x{world}, no collective",
                    "l2": "256 MB memset scrubs L2 before every timed step"},
-        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(frame_bytes),
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_bytes),
                 "host_threads": T, "frames_per_thread": e2e_frames_per_thread,
                 "single_context_ms_per_frame": statistics.median(lat) * 1e3,
-                "path": "trace -> C ABI calls (state machine + recorder) -> H2D -> bin+composite -> D2H RGBA8 into pinned host memory"},
+                "path": "trace -> C ABI calls (state machine + recorder) -> H2D -> bin+composite -> D2H into pinned host memory of "
+                        + ("the YUV 4:2:0 planes (NcrGetBufferAsYUV420P, parity unpinned)" if args.present == "yuv420p" else "the RGB(A)8 frame (GetBufferAsUInt8)")},
         "gpu_launches": int(launches),
         "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
         "roofline": {"bound": "hbm", "kernel": "ncr_composite", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -407,6 +411,8 @@ def main() -> None:
     ap.add_argument("--e2e-threads", type=int, default=0)
     ap.add_argument("--e2e-frames", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--present", default="u8", choices=["u8", "yuv420p"],
+                    help="what the e2e leg reads back per frame: the RGB(A)8 image (reference ABI) or the YUV 4:2:0 planes")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

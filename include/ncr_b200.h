@@ -79,7 +79,7 @@ Texture* CreateMilthmHitEffectTexture(Texture* mask, double seed, double t, doub
 VideoCap* CreateVideoCap(long width, long height, double frameRate);      /* h:87  cpp:65-77 */
 bool InitializeVideoCap(VideoCap* cap, const char* path, bool hasAudio, AudioClip* aClip, long aBitRate); /* h:88 cpp:79-196; false: built without FFmpeg */
 void DestroyVideoCap(VideoCap* cap);                                      /* h:89  cpp:47-50 */
-void PutRendererContextFrame(VideoCap* cap, RenderContext* ctx);          /* h:90  cpp:232-275; flush + u8 present, no encoder */
+void PutRendererContextFrame(VideoCap* cap, RenderContext* ctx);          /* h:90  cpp:232-275; flush + u8 + YUV420P planes on the device, no encoder */
 void ReleaseVideoCap(VideoCap* cap);                                      /* h:91  cpp:198-230 */
 bool PutAudioIntoVideoCap(VideoCap* vCap, AudioClip* aClip, long bitRate); /* h:142 declared, never defined in the reference */
 long GetAudioClipBufferSizeFromData(long numFrames, long channels);       /* h:123 cpp:990-992 */
@@ -144,6 +144,13 @@ void NcrClearClipRect(RenderContext* ctx);
 void NcrSetSampling(RenderContext* ctx, int mode); /* 0 nearest (reference), 1 bilinear (the formula commented out at cpp:575-620) */
 void NcrFillPolygon(RenderContext* ctx, const double* xy, long n_points, double r, double g, double b, double a); /* cpp:822-845 rule, N points */
 void NcrDrawTexturePerspective(RenderContext* ctx, Texture* tex, const double inv_h[9], double x, double y, double width, double height);
+/* Present path (replaces the f64->u8 loop + sws_scale of PutRendererContextFrame, h:91 cpp:232-256, for
+ * cap size == canvas size): flush, convert the canvas to the (iu8)(v*255) image and to planar YUV 4:2:0 (BT.601 studio
+ * swing, 2x2-mean chroma) on the device, and read back only the planes: Y[h][w], U[ch][cw], V[ch][cw] with
+ * cw = (w+1)/2, ch = (h+1)/2, contiguous in `out`.  Returns the bytes written (NcrYUV420PSize), -1 on failure.
+ * libswscale's exact rounding cannot be checked here (FFmpeg absent): parity unpinned. */
+long NcrYUV420PSize(RenderContext* ctx);
+long NcrGetBufferAsYUV420P(RenderContext* ctx, unsigned char* out);
 
 #ifdef __cplusplus
 }

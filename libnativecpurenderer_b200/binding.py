@@ -95,6 +95,8 @@ _EXT_ABI = {
     "NcrDrawTexturePerspective": (None, (_P, _P, _P) + (_D,) * 4),
     "NcrKernelLaunchCount": (c_ulonglong, ()),
     "NcrMeasureF64Rate": (c_double, ()),
+    "NcrYUV420PSize": (c_long, (_P,)),
+    "NcrGetBufferAsYUV420P": (c_long, (_P, _P)),
 }
 
 
@@ -362,6 +364,21 @@ class RenderContext:
         flat = [float(v) for p in points for v in p]
         arr = (c_double * len(flat))(*flat)
         self._lib.NcrFillPolygon(self._ptr, arr, len(flat) // 2, r, g, b, a)
+
+    def get_buffer_as_yuv420p(self, out=None):
+        """Present path: planar Y, U, V of the canvas as one uint8 array (parity unpinned, see include/ncr_b200.h)."""
+        import numpy as np
+
+        n = self._lib.NcrYUV420PSize(self._ptr)
+        if out is None:
+            out = np.empty(n, dtype=np.uint8)
+        got = self._lib.NcrGetBufferAsYUV420P(self._ptr, _as_void_p(out))
+        if got != n:
+            raise RuntimeError("NcrGetBufferAsYUV420P failed")
+        return out
+
+    def get_buffer_as_yuv420p_into(self, address: int) -> int:
+        return self._lib.NcrGetBufferAsYUV420P(self._ptr, c_void_p(address))
 
     def draw_texture_perspective(self, tex: "Texture", inv_h, x, y, w, h):
         arr = (c_double * 9)(*[float(v) for v in inv_h])

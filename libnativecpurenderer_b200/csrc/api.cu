@@ -198,6 +198,7 @@ struct NcrContext {
     DevVec<double> d_aux;
     DevVec<uint32_t> d_coarse, d_coarse_off, d_fine, d_fine_off, d_cursors;
     DevVec<unsigned char> d_u8;
+    DevVec<unsigned char> d_yuv;
     bool u8_valid = false;
     uint32_t* h_cursors = nullptr;   // pinned, 8 words
     bool cursors_pending = false;
@@ -559,7 +560,7 @@ void DestroyRenderContext(RenderContext* ctx) {
     c->last_refs.clear();
     c->d_cmds.release(); c->d_boxes.release(); c->d_aux.release();
     c->d_coarse.release(); c->d_coarse_off.release(); c->d_fine.release(); c->d_fine_off.release();
-    c->d_cursors.release(); c->d_u8.release();
+    c->d_cursors.release(); c->d_u8.release(); c->d_yuv.release();
     for (int k = 0; k < 2; ++k) {
         c->stg[k].cmds.release(); c->stg[k].boxes.release(); c->stg[k].aux.release();
         if (c->stg[k].done) cudaEventDestroy(c->stg[k].done);
@@ -601,6 +602,29 @@ void GetBufferAsUInt8(RenderContext* ctx, unsigned char* buffer) {
     if (bytes && !CK(cudaMemcpyAsync(buffer, c->d_u8.p, bytes, cudaMemcpyDeviceToHost, c->stream))) c->failed = true;
     c->stats.d2h_bytes += bytes;
     sync_ctx(c);
+}
+
+long NcrYUV420PSize(RenderContext* ctx) {
+    NcrContext* c = live(ctx);
+    if (!c || c->w <= 0 || c->h <= 0) return 0;
+    return (long)(c->w * c->h + 2 * ((c->w + 1) / 2) * ((c->h + 1) / 2));
+}
+
+// Present path: flush with the fused u8 image, convert it to planar YUV 4:2:0 on the same stream, read back 1.5 B/px.
+long NcrGetBufferAsYUV420P(RenderContext* ctx, unsigned char* out) {
+    NcrContext* c = live(ctx);
+    if (!c || !out) return -1;
+    const long bytes = NcrYUV420PSize(ctx);
+    if (bytes <= 0) return 0;
+    if (!flush(c, true)) return -1;
+    if (!c->d_yuv.reserve((size_t)bytes)) { c->failed = true; return -1; }
+    ncr_launch_yuv420p(c->d_u8.p, c->d_yuv.p, (int)c->w, (int)c->h, ipp_of(c), c->stream);
+    g_launches += 1;
+    c->stats.kernel_launches += 1;
+    if (!CK(cudaGetLastError()) ||
+        !CK(cudaMemcpyAsync(out, c->d_yuv.p, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream))) { c->failed = true; return -1; }
+    c->stats.d2h_bytes += (size_t)bytes;
+    return sync_ctx(c) ? bytes : -1;
 }
 
 void GetColor(RenderContext* ctx, double x, double y, double* out_r, double* out_g, double* out_b, double* out_a) {

@@ -4,7 +4,7 @@
 //     is worth a GPU;
 //   * the MP4 writer entry points (reference cpp:59-275).  FFmpeg is not part of this build, so the encoder is
 //     absent: InitializeVideoCap reports failure, and PutRendererContextFrame performs the present-side
-//     work that IS on the path (flush + fused f64->u8 image on the device + readback) and drops the frame.
+//     work that IS on the path (flush + fused f64->u8 image + YUV 4:2:0 planes on the device, 1.5 B/px readback) and drops the frame.
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -225,10 +225,12 @@ void DestroyVideoCap(VideoCap* cap) { (void)cap; /* reference: no-op (cpp:47-50)
 
 void PutRendererContextFrame(VideoCap* cap, RenderContext* ctx) {
     if (!cap || !ctx) return;
-    const long n = GetBufferSize(ctx);
+    // cpp:232-256: f64 -> u8 truncation, then RGB(A) -> YUV420P for the encoder.  Both steps run on the device and only
+    // the planes (1.5 B/px) come back; with no encoder linked (FFmpeg absent) the frame is kept as `last` and counted.
+    const long n = NcrYUV420PSize(ctx);
     if (n <= 0) return;
     cap->last.resize((size_t)n);
-    GetBufferAsUInt8(ctx, cap->last.data());   // cpp:236-239: the f64->u8 image every present starts with
+    if (NcrGetBufferAsYUV420P(ctx, cap->last.data()) != n) return;
     cap->frames += 1;
 }
 

@@ -3,6 +3,7 @@
 //   ncr_bin_coarse   commands -> ordered per-128x128-px bin lists      (CTA per bin)
 //   ncr_bin_fine     bin lists -> ordered per-16x16-px tile lists      (warp per tile, ballot + popc compaction)
 //   ncr_convert_u8   f64 canvas -> (iu8)(v*255) image                  (readback of an already flushed canvas)
+//   ncr_yuv420p      u8 image -> planar YUV 4:2:0                       (present path, 1.5 B/px leave the GPU)
 //   ncr_resample     ResampleTexture (reference cpp:950-976)
 //
 // Arithmetic contract (DESIGN.md "Exactness"): round-to-nearest mul/add/sub/div intrinsics only, which the
@@ -152,6 +153,48 @@ __global__ void __launch_bounds__(256) ncr_convert_u8(const double* __restrict__
     for (; k < n; k += stride) out[k] = ncr_to_u8(fb[k]);
 }
 
+// Present path: the (iu8)(v*255) image -> planar YUV 4:2:0, the format PutRendererContextFrame hands to the
+// encoder (reference cpp:232-256: f64 -> u8 truncation, then sws_scale to AV_PIX_FMT_YUV420P).  libswscale is a third-party
+// dependency that is absent here, so its exact rounding cannot be pinned ("parity unpinned"); this kernel implements the
+// published BT.601 studio-swing integer matrix (the 8-bit-shift coefficients of swscale's own rgb24toyv12 C path):
+//     Y = ((66 R + 129 G + 25 B + 128) >> 8) + 16      for every pixel
+//     U = ((-38 R - 74 G + 112 B + 128) >> 8) + 128    V = ((112 R - 94 G - 18 B + 128) >> 8) + 128
+// with U, V taken from the rounded mean (sum + 2) >> 2 of each 2x2 block (edge blocks of odd-sized images replicate the
+// last column / row).  Alpha is ignored, as AV_PIX_FMT_RGBA -> YUV420P does.  One thread per 2x2 block; 1.5 bytes per pixel
+// leave the GPU instead of 3 or 4.
+template <int IPP>
+__global__ void __launch_bounds__(256) ncr_yuv420p(const unsigned char* __restrict__ img, unsigned char* __restrict__ out,
+                                                   int w, int h) {
+    const int cw = (w + 1) >> 1, ch = (h + 1) >> 1;
+    const int bx = blockIdx.x * 32 + (threadIdx.x & 31), by = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (bx >= cw || by >= ch) return;
+    unsigned char* Y = out;
+    unsigned char* U = out + (size_t)w * h;
+    unsigned char* V = U + (size_t)cw * ch;
+    int sr = 0, sg = 0, sb = 0;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            const int x = min(2 * bx + dx, w - 1), y = min(2 * by + dy, h - 1);
+            int r, g, b;
+            if (IPP == 4) {
+                const uint32_t t = __ldg((const uint32_t*)img + (size_t)y * w + x);
+                r = t & 255u; g = (t >> 8) & 255u; b = (t >> 16) & 255u;
+            } else {
+                const unsigned char* q = img + ((size_t)y * w + x) * 3;
+                r = __ldg(q); g = __ldg(q + 1); b = __ldg(q + 2);
+            }
+            sr += r; sg += g; sb += b;
+            if (2 * bx + dx < w && 2 * by + dy < h)
+                Y[(size_t)y * w + x] = (unsigned char)(((66 * r + 129 * g + 25 * b + 128) >> 8) + 16);
+        }
+    }
+    const int r = (sr + 2) >> 2, g = (sg + 2) >> 2, b = (sb + 2) >> 2;
+    U[(size_t)by * cw + bx] = (unsigned char)(((-38 * r - 74 * g + 112 * b + 128) >> 8) + 128);
+    V[(size_t)by * cw + bx] = (unsigned char)(((112 * r - 94 * g - 18 * b + 128) >> 8) + 128);
+}
+
 // ResampleTexture, reference cpp:950-976: out(i,j) = nearest(in, (f64)i / width * in.w, (f64)j / height * in.h).
 __global__ void __launch_bounds__(256) ncr_resample(NcrCmd src, void* out, int ow, int oh) {
     const int i = blockIdx.x * 16 + (threadIdx.x & 15);
@@ -201,6 +244,13 @@ extern "C" void ncr_launch_convert_u8(const double* fb, unsigned char* out, size
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
     ncr_convert_u8<<<blocks, 256, 0, s>>>(fb, out, n);
+}
+
+extern "C" void ncr_launch_yuv420p(const unsigned char* img, unsigned char* out, int w, int h, int ipp, cudaStream_t s) {
+    if (w <= 0 || h <= 0) return;
+    dim3 grid(((w + 1) / 2 + 31) / 32, ((h + 1) / 2 + 7) / 8);
+    if (ipp == 4) ncr_yuv420p<4><<<grid, 256, 0, s>>>(img, out, w, h);
+    else ncr_yuv420p<3><<<grid, 256, 0, s>>>(img, out, w, h);
 }
 
 extern "C" void ncr_launch_resample(const NcrCmd* src, void* out, int ow, int oh, cudaStream_t s) {

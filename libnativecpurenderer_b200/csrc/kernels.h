@@ -15,6 +15,7 @@ extern "C" {
 void ncr_launch_flush(const NcrFlushArgs* A, cudaStream_t s, cudaEvent_t* ev);
 void ncr_launch_composite(const NcrFlushArgs* A, cudaStream_t s);
 void ncr_launch_convert_u8(const double* fb, unsigned char* out, size_t n, cudaStream_t s);
+void ncr_launch_yuv420p(const unsigned char* img, unsigned char* out, int w, int h, int ipp, cudaStream_t s);
 void ncr_launch_resample(const NcrCmd* src, void* out, int ow, int oh, cudaStream_t s);
 double ncr_measure_f64_rate(cudaStream_t s);   // non-fused DMUL+DADD instructions per second
 }

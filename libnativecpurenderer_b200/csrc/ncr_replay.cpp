@@ -54,6 +54,8 @@ struct Api {
     void (*NcrSetSampling)(H, int) = nullptr;
     void (*NcrFillPolygon)(H, const double*, long, double, double, double, double) = nullptr;
     void (*NcrDrawTexturePerspective)(H, H, const double*, double, double, double, double) = nullptr;
+    long (*NcrGetBufferAsYUV420P)(H, unsigned char*) = nullptr;
+    int present_mode = 0;   // 0: PRESENT reads back the u8 image (GetBufferAsUInt8); 1: the YUV 4:2:0 planes (video present path)
 };
 
 template <class F>
@@ -105,7 +107,10 @@ long run_trace(const Api& a, H ctx, const unsigned char* p, long bytes, H const*
                 a.ApplyPixel(ctx, (long)v[0], (long)v[1], v[2], v[3], v[4], v[5]);
                 break;
             case NCR_T_PRESENT:
-                if (frame) a.GetBufferAsUInt8(ctx, frame);
+                if (frame) {
+                    if (a.present_mode == 1 && a.NcrGetBufferAsYUV420P) a.NcrGetBufferAsYUV420P(ctx, frame);
+                    else a.GetBufferAsUInt8(ctx, frame);
+                }
                 if (presents) ++*presents;
                 break;
             case NCR_T_CLIP_SET:
@@ -166,11 +171,21 @@ void* ncr_replay_open(const char* path) {
     bind(dl, "NcrSetSampling", a->NcrSetSampling, false);
     bind(dl, "NcrFillPolygon", a->NcrFillPolygon, false);
     bind(dl, "NcrDrawTexturePerspective", a->NcrDrawTexturePerspective, false);
+    bind(dl, "NcrGetBufferAsYUV420P", a->NcrGetBufferAsYUV420P, false);
     if (!ok) {
         delete a;
         return nullptr;
     }
     return a;
+}
+
+// PRESENT records read back the u8 image (mode 0, the reference ABI) or the YUV 4:2:0 planes (mode 1, product only).
+// Returns 0, or -1 when the library has no YUV entry point.
+int ncr_replay_set_present(void* api, int mode) {
+    Api* a = (Api*)api;
+    if (mode == 1 && !a->NcrGetBufferAsYUV420P) return -1;
+    a->present_mode = mode;
+    return 0;
 }
 
 // Replays `trace` `repeats` times on an existing context.  frame (may be null) receives every PRESENT readback.

@@ -146,9 +146,16 @@ class Replayer:
         self.lib.ncr_replay_run_threads.restype = ctypes.c_double
         self.lib.ncr_replay_run_threads.argtypes = (ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_int,
                                                     ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_int)
+        self.lib.ncr_replay_set_present.restype = ctypes.c_int
+        self.lib.ncr_replay_set_present.argtypes = (ctypes.c_void_p, ctypes.c_int)
         self.api = self.lib.ncr_replay_open(target_lib_path.encode())
         if not self.api:
             raise OSError(f"cannot bind {target_lib_path}")
+
+    def set_present(self, mode: str) -> None:
+        """What a PRESENT record reads back: "u8" (GetBufferAsUInt8, the reference ABI) or "yuv420p" (NcrGetBufferAsYUV420P)."""
+        if self.lib.ncr_replay_set_present(self.api, {"u8": 0, "yuv420p": 1}[mode]) != 0:
+            raise OSError("target library has no NcrGetBufferAsYUV420P")
 
     def run(self, ctx, trace: np.ndarray, textures, frame_address: int | None = None, repeats: int = 1) -> float:
         table = texture_table(textures)

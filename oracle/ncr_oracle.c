@@ -572,3 +572,49 @@ void NcrDrawTexturePerspective(Canvas* c, Image* tex, const f64* hinv, f64 x, f6
     raster(c, all, &s);
     release_operand(t);
 }
+
+/* ---------------------------------------------------------------- present path — PARITY UNPINNED
+ * PutRendererContextFrame (cpp:232-256) truncates the canvas to u8 and hands it to libswscale for RGB(A) -> YUV420P.
+ * libswscale (FFmpeg, un-vendored third-party dependency; the reference pins no version) is absent here, so its exact
+ * rounding cannot be reproduced or checked.  This restates the published BT.601 studio-swing 8-bit integer matrix
+ *   Y = ((66R + 129G + 25B + 128) >> 8) + 16,  U = ((-38R - 74G + 112B + 128) >> 8) + 128,
+ *   V = ((112R - 94G - 18B + 128) >> 8) + 128
+ * (known answers: black 16/128/128, white 235/128/128, red 82/90/240, green 144/54/34, blue 41/240/110), with chroma
+ * from the rounded mean of each 2x2 block and edge replication for odd sizes.  It only checks the product against this
+ * repo's own definition. */
+static int floor_shift8(int v) { return (v >= 0) ? (v >> 8) : -((-v + 255) >> 8); }   /* floor(v / 256) without relying on signed >> */
+long NcrYUV420PSize(Canvas* c) {
+    if (c->w <= 0 || c->h <= 0) return 0;
+    return (long)(c->w * c->h + 2 * ((c->w + 1) / 2) * ((c->h + 1) / 2));
+}
+long NcrGetBufferAsYUV420P(Canvas* c, u8* out) {
+    const i64 w = c->w, h = c->h, cw = (w + 1) / 2, ch = (h + 1) / 2;
+    const int ipp = c->ipp;
+    if (w <= 0 || h <= 0) return 0;
+    u8* img = (u8*)malloc((size_t)(w * h * ipp));
+    if (!img) return -1;
+    GetBufferAsUInt8(c, img);
+    u8 *Y = out, *U = out + w * h, *V = U + cw * ch;
+    for (i64 j = 0; j < h; ++j)
+        for (i64 i = 0; i < w; ++i) {
+            const u8* q = img + (j * w + i) * ipp;
+            Y[j * w + i] = (u8)(floor_shift8(66 * q[0] + 129 * q[1] + 25 * q[2] + 128) + 16);
+        }
+    for (i64 bj = 0; bj < ch; ++bj)
+        for (i64 bi = 0; bi < cw; ++bi) {
+            int sum[3] = {0, 0, 0};
+            for (int dy = 0; dy < 2; ++dy)
+                for (int dx = 0; dx < 2; ++dx) {
+                    i64 x = 2 * bi + dx, y = 2 * bj + dy;
+                    if (x > w - 1) x = w - 1;
+                    if (y > h - 1) y = h - 1;
+                    const u8* q = img + (y * w + x) * ipp;
+                    for (int k = 0; k < 3; ++k) sum[k] += q[k];
+                }
+            const int r = (sum[0] + 2) / 4, g = (sum[1] + 2) / 4, b = (sum[2] + 2) / 4;
+            U[bj * cw + bi] = (u8)(floor_shift8(-38 * r - 74 * g + 112 * b + 128) + 128);
+            V[bj * cw + bi] = (u8)(floor_shift8(112 * r - 94 * g - 18 * b + 128) + 128);
+        }
+    free(img);
+    return NcrYUV420PSize(c);
+}

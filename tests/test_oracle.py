@@ -80,3 +80,26 @@ def test_u8_truncation_edge_values(port, ref):
         ctx.set_pixel(2, 0, vals[8], vals[9], 0, 0)
         got.append(list(ctx.get_buffer_as_uint8()[:12]))
     assert got[0] == got[1] == [254, 254, 0, 44, 0, 0, 255, 254, 159, 85, 0, 0]
+
+
+def test_yuv420p_restatement_known_answers(port):
+    """Present path, PARITY UNPINNED against libswscale (absent): the restatement reproduces the published
+    BT.601 studio-swing known answers for the primaries, on RGB and RGBA canvases, with odd sizes (edge replication)."""
+    kat = {(0, 0, 0): (16, 128, 128), (1, 1, 1): (235, 128, 128), (1, 0, 0): (82, 90, 240), (0, 1, 0): (144, 54, 34),
+           (0, 0, 1): (41, 240, 110)}
+    for alpha in (True, False):
+        for (r, g, b), (y, u, v) in kat.items():
+            ctx = port.RenderContext(5, 3, alpha)
+            ctx.set_color(0.5, 0.5, 0.5, 0.5)
+            ctx.fill_color(r, g, b, 1.0)
+            out = ctx.get_buffer_as_yuv420p()
+            assert out.size == 5 * 3 + 2 * 3 * 2
+            assert set(out[:15]) == {y} and set(out[15:21]) == {u} and set(out[21:]) == {v}
+    # chroma is the rounded 2x2 mean, luma is per pixel
+    ctx = port.RenderContext(2, 2, True)
+    ctx.set_color(0, 0, 0, 1)
+    ctx.set_pixel(0, 0, 1, 0, 0, 1)
+    out = ctx.get_buffer_as_yuv420p()
+    assert list(out[:4]) == [82, 16, 16, 16]
+    r = (255 + 2) // 4
+    assert out[4] == ((-38 * r + 128) >> 8) + 128 and out[5] == ((112 * r + 128) >> 8) + 128

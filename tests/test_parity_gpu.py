@@ -405,3 +405,55 @@ def test_perspective_pixel_box_is_conservative(gpu, port):
         streams.stream_c3p(ctx, atlas, n=400, cells=4)
         got.append(cases.digest(ctx))
     assert got[0] == got[1]
+
+
+@pytest.mark.parametrize("shape", [(160, 90, True), (97, 61, False), (257, 129, True), (2, 2, False), (1, 1, True)])
+def test_yuv420p_present_matches_port_parity_unpinned(shape, gpu, port, image_rgba):
+    """Present path: NcrGetBufferAsYUV420P (flush + fused u8 image + ncr_yuv420p + 1.5 B/px readback) against
+    the C restatement on the same random stream.  PARITY UNPINNED w.r.t. libswscale (third-party, absent); the u8 image
+    the planes are computed from IS pinned (it is GetBufferAsUInt8's)."""
+    w, h, alpha = shape
+    got = []
+    for R in (gpu, port):
+        ctx = R.RenderContext(w, h, alpha)
+        tex = cases.tiny_textures(R, image_rgba)
+        streams.stream_random(ctx, tex, 77, n=60)
+        yuv = ctx.get_buffer_as_yuv420p()
+        assert yuv.size == w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2)
+        got.append((yuv.tobytes(), cases.digest(ctx)))
+    assert got[0] == got[1]
+
+
+def test_yuv420p_full_size_and_video_cap_path(gpu):
+    """1080p RGB chart frame (the milrenderer shape): planes are consistent with the u8 image of the same canvas, and
+    PutRendererContextFrame (h:91) drives the same path."""
+    w, h = 1920, 1080
+    chart = streams.make_chart_textures()
+    bg = np.ascontiguousarray(np.resize(streams.make_noise_texture(256, 7), (h, w, 4)))
+    tex_np = [bg] + chart
+    tex = [gpu.Texture.from_numpy(t) for t in tex_np]
+    ctx = gpu.RenderContext(w, h, False)
+    rec = trace.TraceRecorder(w, h, False)
+    slots = [trace.TexSlot(k, t.shape[1], t.shape[0]) for k, t in enumerate(tex_np)]
+    streams.stream_c4_frame(rec, slots[0], slots[1:], frame=7, n_notes=300)
+    trace.submit_trace(ctx, rec.as_array(), tex)
+    yuv = ctx.get_buffer_as_yuv420p()
+    img = ctx.get_buffer_as_uint8().reshape(h, w, 3).astype(np.int32)
+    y = ((66 * img[..., 0] + 129 * img[..., 1] + 25 * img[..., 2] + 128) >> 8) + 16
+    assert np.array_equal(yuv[: w * h].reshape(h, w), y.astype(np.uint8))
+    m = (img.reshape(h // 2, 2, w // 2, 2, 3).sum(axis=(1, 3)) + 2) >> 2
+    u = ((-38 * m[..., 0] - 74 * m[..., 1] + 112 * m[..., 2] + 128) >> 8) + 128
+    v = ((112 * m[..., 0] - 94 * m[..., 1] - 18 * m[..., 2] + 128) >> 8) + 128
+    assert np.array_equal(yuv[w * h: w * h + w * h // 4].reshape(h // 2, w // 2), u.astype(np.uint8))
+    assert np.array_equal(yuv[w * h + w * h // 4:].reshape(h // 2, w // 2), v.astype(np.uint8))
+    raw = ctypes.CDLL(gpu.path)   # the video entry points are not part of the render binding: plain ctypes, as pyb:425-478 does
+    raw.CreateVideoCap.restype = ctypes.c_void_p
+    raw.CreateVideoCap.argtypes = (ctypes.c_long, ctypes.c_long, ctypes.c_double)
+    raw.PutRendererContextFrame.argtypes = (ctypes.c_void_p, ctypes.c_void_p)
+    raw.DestroyVideoCap.argtypes = (ctypes.c_void_p,)
+    cap = raw.CreateVideoCap(w, h, 60.0)
+    assert cap
+    d2h0 = ctx.stats().d2h_bytes
+    raw.PutRendererContextFrame(cap, ctx._ptr)
+    assert ctx.stats().d2h_bytes - d2h0 == w * h * 3 // 2   # 1.5 B/px leave the GPU, not 3
+    raw.DestroyVideoCap(cap)
