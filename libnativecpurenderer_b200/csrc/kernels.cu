@@ -246,8 +246,54 @@ extern "C" void ncr_launch_convert_u8(const double* fb, unsigned char* out, size
     ncr_convert_u8<<<blocks, 256, 0, s>>>(fb, out, n);
 }
 
+// Same conversion for widths that are a multiple of 8 (1080p, 4K): one thread per 8x2 pixel block, 64-bit / 128-bit loads
+// of the image rows, one 8-byte store per luma row and one 4-byte store per chroma plane.
+template <int IPP>
+__global__ void __launch_bounds__(256) ncr_yuv420p_w8(const unsigned char* __restrict__ img, unsigned char* __restrict__ out,
+                                                      int w, int h) {
+    const int ch = (h + 1) >> 1, cw = w >> 1, w8 = w >> 3;
+    const int bx = blockIdx.x * 32 + (threadIdx.x & 31), by = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (bx >= w8 || by >= ch) return;
+    unsigned char* Y = out;
+    unsigned char* U = out + (size_t)w * h;
+    unsigned char* V = U + (size_t)cw * ch;
+    int sr[4] = {0, 0, 0, 0}, sg[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+        const int yr = 2 * by + dy, y = min(yr, h - 1);
+        unsigned char px[8 * IPP];
+        const unsigned char* row = img + ((size_t)y * w + 8 * bx) * IPP;   // 8*IPP bytes, 8-byte aligned because w % 8 == 0
+#pragma unroll
+        for (int k = 0; k < IPP; ++k) ((uint2*)px)[k] = __ldg((const uint2*)row + k);
+        unsigned char ly[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = px[i * IPP], g = px[i * IPP + 1], b = px[i * IPP + 2];
+            sr[i >> 1] += r; sg[i >> 1] += g; sb[i >> 1] += b;
+            ly[i] = (unsigned char)(((66 * r + 129 * g + 25 * b + 128) >> 8) + 16);
+        }
+        if (yr < h) *(uint2*)(Y + (size_t)y * w + 8 * bx) = *(const uint2*)ly;
+    }
+    unsigned char lu[4], lv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = (sr[k] + 2) >> 2, g = (sg[k] + 2) >> 2, b = (sb[k] + 2) >> 2;
+        lu[k] = (unsigned char)(((-38 * r - 74 * g + 112 * b + 128) >> 8) + 128);
+        lv[k] = (unsigned char)(((112 * r - 94 * g - 18 * b + 128) >> 8) + 128);
+    }
+    *(uint32_t*)(U + (size_t)by * cw + 4 * bx) = *(const uint32_t*)lu;
+    *(uint32_t*)(V + (size_t)by * cw + 4 * bx) = *(const uint32_t*)lv;
+}
+
 extern "C" void ncr_launch_yuv420p(const unsigned char* img, unsigned char* out, int w, int h, int ipp, cudaStream_t s) {
     if (w <= 0 || h <= 0) return;
+    // the vector variant needs every row, the luma plane and both chroma planes to start on the alignment of its accesses
+    if (w % 8 == 0 && (((size_t)w * h) % 8 == 0) && ((((size_t)w / 2) * ((h + 1) / 2)) % 4 == 0)) {
+        dim3 grid((w / 8 + 31) / 32, ((h + 1) / 2 + 7) / 8);
+        if (ipp == 4) ncr_yuv420p_w8<4><<<grid, 256, 0, s>>>(img, out, w, h);
+        else ncr_yuv420p_w8<3><<<grid, 256, 0, s>>>(img, out, w, h);
+        return;
+    }
     dim3 grid(((w + 1) / 2 + 31) / 32, ((h + 1) / 2 + 7) / 8);
     if (ipp == 4) ncr_yuv420p<4><<<grid, 256, 0, s>>>(img, out, w, h);
     else ncr_yuv420p<3><<<grid, 256, 0, s>>>(img, out, w, h);

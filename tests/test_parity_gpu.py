@@ -407,7 +407,7 @@ def test_perspective_pixel_box_is_conservative(gpu, port):
     assert got[0] == got[1]
 
 
-@pytest.mark.parametrize("shape", [(160, 90, True), (97, 61, False), (257, 129, True), (2, 2, False), (1, 1, True)])
+@pytest.mark.parametrize("shape", [(160, 90, True), (160, 90, False), (97, 61, False), (257, 129, True), (2, 2, False), (1, 1, True), (8, 3, True), (24, 5, False)])
 def test_yuv420p_present_matches_port_parity_unpinned(shape, gpu, port, image_rgba):
     """Present path: NcrGetBufferAsYUV420P (flush + fused u8 image + ncr_yuv420p + 1.5 B/px readback) against
     the C restatement on the same random stream.  PARITY UNPINNED w.r.t. libswscale (third-party, absent); the u8 image
@@ -438,7 +438,7 @@ def test_yuv420p_full_size_and_video_cap_path(gpu):
     streams.stream_c4_frame(rec, slots[0], slots[1:], frame=7, n_notes=300)
     trace.submit_trace(ctx, rec.as_array(), tex)
     yuv = ctx.get_buffer_as_yuv420p()
-    img = ctx.get_buffer_as_uint8().reshape(h, w, 3).astype(np.int32)
+    img = np.frombuffer(ctx.get_buffer_as_uint8(), dtype=np.uint8).reshape(h, w, 3).astype(np.int32)
     y = ((66 * img[..., 0] + 129 * img[..., 1] + 25 * img[..., 2] + 128) >> 8) + 16
     assert np.array_equal(yuv[: w * h].reshape(h, w), y.astype(np.uint8))
     m = (img.reshape(h // 2, 2, w // 2, 2, 3).sum(axis=(1, 3)) + 2) >> 2
