@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the draw/composite hot path (contract: task statement §④, DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl product|reference] [--workload c2|c1|c3|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl product|reference] [--workload c2|c1|c3|c4|c5|bg|c2x|c3p] [--present u8|yuv420p]
 
 A *step* is one frame of the workload: the whole recorded command stream of one canvas is binned and
 composited (ncr_bin_coarse -> ncr_bin_fine -> ncr_composite with the fused u8 image).
@@ -51,6 +51,8 @@ WORKLOADS = {
                               "perspective-warped sprites from a 2048^2 atlas via NcrDrawTexturePerspective"),
     "bg": (1920, 1080, True, "low-overdraw end of the path: 1920x1080 RGBA, SetColor + full-screen DrawTexture (identity path) + FillColor "
                             "dim, u8 readback (3 commands per tile; the HBM-leaning regime)"),
+    "c5": (3840, 2160, False, "BASELINE config 5 frame (SURVEY C5): 3840x2160 RGB milrenderer-shaped chart frame (C4's generator at 4K), "
+                              "~1,500 notes, 12 lines, 100 hit effects, u8 readback; frames are sharded across ranks"),
     "c4": (1920, 1080, False, "BASELINE config 4 frame (SURVEY C4): 1920x1080 RGB milrenderer-shaped chart frame, ~1,500 notes, "
                               "12 lines, 100 hit effects, u8 readback"),
 }
@@ -89,7 +91,7 @@ def build_workload(name: str, n_draws: int | None = None):
         rec.set_color(0, 0, 0, 1)
         rec.draw_texture(slot, 0, 0, w, h)
         rec.fill_color(0, 0, 0, .6)
-    elif name == "c4":
+    elif name in ("c4", "c5"):
         chart = streams.make_chart_textures()
         bg = np.ascontiguousarray(np.resize(streams.make_noise_texture(256, 7), (h, w, 4)))
         tex_np = [bg] + chart
@@ -214,7 +216,7 @@ def run_reference(args) -> None:
     if args.workload in ("c2x", "c3p"):
         print(json.dumps({"impl": "reference", "unavailable": "the reference has no clip/bilinear/polygon/perspective entry points"}))
         return
-    per_frame_s = {"c1": 1.1, "c2": 16.0, "c3": 60.0, "c4": 3.0, "bg": 0.1}[args.workload]
+    per_frame_s = {"c1": 1.1, "c2": 16.0, "c3": 60.0, "c4": 3.0, "c5": 12.0, "bg": 0.1}[args.workload]
     budget = 150.0 / max(1, args.steps + args.warmup)
     sample = int(max(min(full, 200), min(full, full * budget / per_frame_s)))
     fps, kind, text, step_s = cpu_arm(args.workload, threads, sample, args.steps, args.warmup)
@@ -380,7 +382,7 @@ def run_product(args) -> None:
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload not in ("c2x", "c3p"):
         threads = min(host_threads(), 64)
-        sample = {"c1": 1000, "c2": 20000, "c3": 12000, "c4": 1500, "bg": 2}[args.workload]
+        sample = {"c1": 1000, "c2": 20000, "c3": 12000, "c4": 1500, "c5": 1500, "bg": 2}[args.workload]
         fps, kind, text, _ = cpu_arm(args.workload, threads, sample, 1, 0)
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind, "sample": text}
     elif rank == 0:
