@@ -42,10 +42,13 @@ __device__ __noinline__ double ncr_sqrt(double a) { return __dsqrt_rn(a); }
 #ifndef NCR_NX
 #define NCR_NX 2
 #endif
+#ifndef NCR_NY
 #define NCR_NY 2
+#endif
+#define NCR_RH (4 * NCR_NY)                      // region height in pixels
 #define NCR_P (NCR_NX * NCR_NY)
 #define NCR_RW (8 * NCR_NX)                      // region width in pixels
-#define NCR_TASKS_PER_TILE ((16 / NCR_RW) * 2)   // regions per 16x16 tile
+#define NCR_TASKS_PER_TILE ((16 / NCR_RW) * (16 / (4 * NCR_NY)))   // regions per 16x16 tile
 #define SX(p) ((p) % NCR_NX)
 #define SY(p) ((p) / NCR_NX)
 #ifndef NCR_COMPOSITE_MIN_CTAS
@@ -504,8 +507,13 @@ __global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, NCR_COMPOSITE_MIN_CTAS)
     double* s_lut = (double*)ncr_smem;
     // Per-warp double-buffered command slot: the next command of the list is fetched while the current one is applied.
     NcrCmd (*s_cmd)[2] = (NcrCmd (*)[2])(ncr_smem + NCR_LUT_BYTES);
-    for (int e = threadIdx.x; e < 256 * NCR_LUT_COPIES; e += NCR_COMPOSITE_THREADS)
-        s_lut[e] = DIV((double)(e / NCR_LUT_COPIES), 255.0);
+    // One division per entry (256 per CTA, not 256 x copies: the init is ~10 % of a low-overdraw launch otherwise), then
+    // each value is replicated by its thread.
+    for (int k = threadIdx.x; k < 256; k += NCR_COMPOSITE_THREADS) {
+        const double v = DIV((double)k, 255.0);
+#pragma unroll 8
+        for (int c = 0; c < NCR_LUT_COPIES; ++c) s_lut[k * NCR_LUT_COPIES + ((c + k) & (NCR_LUT_COPIES - 1))] = v;
+    }
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -530,7 +538,7 @@ __global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, NCR_COMPOSITE_MIN_CTAS)
         if (lcount == 0 && A.u8_out == nullptr) continue;
 
         const int x0 = (tile % A.d.tiles_x) * NCR_TILE + (sub % (16 / NCR_RW)) * NCR_RW;
-        const int y0 = (tile / A.d.tiles_x) * NCR_TILE + (sub / (16 / NCR_RW)) * 8;
+        const int y0 = (tile / A.d.tiles_x) * NCR_TILE + (sub / (16 / NCR_RW)) * NCR_RH;
         if (y0 >= H || x0 >= W) continue;
         Slots S;
 #pragma unroll
@@ -565,9 +573,9 @@ __global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, NCR_COMPOSITE_MIN_CTAS)
                 if (k0 + lane < lcount) {
                     mine = __ldg(&A.fine_list[loff + k0 + lane]);
                     const int4 box = __ldg((const int4*)&A.boxes[mine]);   // l, r, t, b
-                    hit = box.z < y0 + 8 && box.w > y0 && box.x < x0 + NCR_RW && box.y > x0;
+                    hit = box.z < y0 + NCR_RH && box.w > y0 && box.x < x0 + NCR_RW && box.y > x0;
                     if (hit) hit = !quad_misses_region(A.cmds + mine, max(x0, box.x), min(x0 + NCR_RW, box.y) - 1,
-                                                       max(y0, box.z), min(y0 + 8, box.w) - 1);
+                                                       max(y0, box.z), min(y0 + NCR_RH, box.w) - 1);
                 }
                 pending = __ballot_sync(FULL, hit);
                 k0 += 32;
