@@ -232,6 +232,12 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+def sharding_frames(n_frames: int, rank: int, world: int):
+    from libnativecpurenderer_b200 import sharding
+
+    return sharding.frames_for_rank(n_frames, rank, world)
+
+
 def metric_name(workload: str) -> str:
     res = "4K" if WORKLOADS[workload][0] == 3840 else "1080p"
     return f"{res} frames/s ({workload})"
@@ -335,6 +341,32 @@ def run_product(args) -> None:
         rp.run(ctx, arr, tex, frame_address=pinned)
         lat.append(time.perf_counter() - t0)
 
+    # ---- optional: N consecutive DISTINCT frames through the batch renderer (BASELINE configs 4/5 as stated) ----
+    video = None
+    if args.video > 0 and args.workload in ("c4", "c5"):
+        from libnativecpurenderer_b200 import batch, streams
+
+        n_video = len(sharding_frames(args.video, rank, world))
+        slots = [trace.TexSlot(k, t.shape[1], t.shape[0]) for k, t in enumerate(tex_np)]
+        vtraces = []
+        for f in sharding_frames(args.video, rank, world):   # this rank's frames (frame f -> rank f mod N, no collective)
+            rec = trace.TraceRecorder(w, h, alpha)
+            streams.stream_c4_frame(rec, slots[0], slots[1:], frame=f, n_notes=full)
+            rec.present()
+            vtraces.append(rec.as_array())
+        seen = []
+        batch.render_frames(R, w, h, alpha, vtraces[: 2 * T], tex, workers=T, present=args.present)   # warm the contexts
+        barrier()
+        t0 = time.perf_counter()
+        batch.render_frames(R, w, h, alpha, vtraces, tex, on_frame=lambda i, px: seen.append(i), workers=T, present=args.present)
+        v_s = time.perf_counter() - t0
+        barrier()
+        assert seen == list(range(n_video))
+        video = {"frames": args.video, "value": args.video / max_over_ranks(v_s), "unit": "frames/s", "workers_per_gpu": T,
+                 "present": args.present, "d2h_bytes_per_frame": int(d2h_bytes),
+                 "h2d_bytes_per_frame": int(h2d),
+                 "path": "N distinct consecutive frames: recorded traces -> NcrRenderFrames (worker contexts, in-order delivery)"}
+
     # ---- roofline of the dominant kernel (ncr_composite) --------------------------------------------------
     peak, peak_src = measured_peak_gbs()
     tex_bytes = sum(int(t.nbytes) for t in tex_np)
@@ -379,6 +411,8 @@ def run_product(args) -> None:
         "device": R.lib.NcrDeviceName().decode(),
         "host_wall_s_value_region": wall_value,
     }
+    if video:
+        line["video"] = video
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload not in ("c2x", "c3p"):
         threads = min(host_threads(), 64)
@@ -413,6 +447,8 @@ def main() -> None:
     ap.add_argument("--e2e-threads", type=int, default=0)
     ap.add_argument("--e2e-frames", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--video", type=int, default=0,
+                    help="c4/c5 only: also render this many DISTINCT consecutive frames through NcrRenderFrames (configs 4/5)")
     ap.add_argument("--present", default="u8", choices=["u8", "yuv420p"],
                     help="what the e2e leg reads back per frame: the RGB(A)8 image (reference ABI) or the YUV 4:2:0 planes")
     args = ap.parse_args()

@@ -149,6 +149,14 @@ void NcrDrawTexturePerspective(RenderContext* ctx, Texture* tex, const double in
  * swing, 2x2-mean chroma) on the device, and read back only the planes: Y[h][w], U[ch][cw], V[ch][cw] with
  * cw = (w+1)/2, ch = (h+1)/2, contiguous in `out`.  Returns the bytes written (NcrYUV420PSize), -1 on failure.
  * libswscale's exact rounding cannot be checked here (FFmpeg absent): parity unpinned. */
+/* Frame-parallel batch render (finishes reference pyb:302-367 MultiThreadedVideoRenderContextPreparer):
+ * n_frames recorded frames (trace format as NcrSubmitTrace) are rendered by n_workers threads with one context / CUDA
+ * stream each and delivered to `sink` strictly in frame order (pixels: the RGB(A)8 image for present 0, the YUV 4:2:0
+ * planes for present 1; valid only during the call).  Every frame must start by overwriting the canvas with SetColor.
+ * Returns n_frames, -1 on a device/trace error, -2 when a frame is not independent. */
+typedef void (*NcrFrameSink)(void* user, long frame_index, const unsigned char* pixels, long bytes);
+long NcrRenderFrames(long width, long height, int alpha, const void* const* traces, const long* trace_bytes, long n_frames,
+                     Texture* const* textures, long n_textures, int n_workers, int present, NcrFrameSink sink, void* user);
 long NcrYUV420PSize(RenderContext* ctx);
 long NcrGetBufferAsYUV420P(RenderContext* ctx, unsigned char* out);
 

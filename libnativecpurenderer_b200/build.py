@@ -20,7 +20,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libNativeCPURenderer.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["api.cu", "kernels.cu", "composite.cu", "host_misc.cpp"]
+SOURCES = ["api.cu", "kernels.cu", "composite.cu", "host_misc.cpp", "batch.cpp"]
 # -fmad=false: the reference's f64 expression trees must not be contracted into FMAs on the device;
 # -ffp-contract=off keeps the host-side per-call math (state.h) uncontracted as well.
 NVCC_FLAGS = [

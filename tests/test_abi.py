@@ -125,3 +125,19 @@ def test_reference_binding_imports_against_the_product_unchanged(tmp_path):
     assert res.returncode == 0, res.stderr
     assert "VERSION 1" in res.stdout and "MISSING []" in res.stdout
     assert "WAV 244 0.00625" in res.stdout
+
+
+def test_batch_render_validates_frames_before_touching_a_device():
+    """NcrRenderFrames: an empty batch is a no-op and a frame that does not start by overwriting the canvas
+    is refused (-2) — both decided on the host, before any context is created."""
+    from libnativecpurenderer_b200 import batch, trace
+    from libnativecpurenderer_b200.binding import Renderer
+
+    R = Renderer()
+    assert batch.render_frames(R, 64, 48, True, [], []) == 0
+    rec = trace.TraceRecorder(64, 48, True)
+    rec.translate(3, 4)
+    rec.fill_color(1, 0, 0, .5)   # reads the previous canvas: not an independent frame
+    rec.present()
+    with pytest.raises(ValueError):
+        batch.render_frames(R, 64, 48, True, [rec.as_array()], [])
