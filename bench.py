@@ -355,12 +355,13 @@ def run_product(args) -> None:
             rec.present()
             vtraces.append(rec.as_array())
         seen = []
-        batch.render_frames(R, w, h, alpha, vtraces[: 2 * T], tex, workers=T, present=args.present)   # warm the contexts
-        barrier()
-        t0 = time.perf_counter()
-        batch.render_frames(R, w, h, alpha, vtraces, tex, on_frame=lambda i, px: seen.append(i), workers=T, present=args.present)
-        v_s = time.perf_counter() - t0
-        barrier()
+        with batch.FramePool(R, w, h, alpha, workers=T) as pool:
+            pool.render(vtraces[: 2 * T], tex, present=args.present)   # warm-up: first-use allocations of every context
+            barrier()
+            t0 = time.perf_counter()
+            pool.render(vtraces, tex, on_frame=lambda i, px: seen.append(i), present=args.present)
+            v_s = time.perf_counter() - t0
+            barrier()
         assert seen == list(range(n_video))
         video = {"frames": args.video, "value": args.video / max_over_ranks(v_s), "unit": "frames/s", "workers_per_gpu": T,
                  "present": args.present, "d2h_bytes_per_frame": int(d2h_bytes),

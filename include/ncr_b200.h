@@ -157,6 +157,13 @@ void NcrDrawTexturePerspective(RenderContext* ctx, Texture* tex, const double in
 typedef void (*NcrFrameSink)(void* user, long frame_index, const unsigned char* pixels, long bytes);
 long NcrRenderFrames(long width, long height, int alpha, const void* const* traces, const long* trace_bytes, long n_frames,
                      Texture* const* textures, long n_textures, int n_workers, int present, NcrFrameSink sink, void* user);
+/* The same with the worker contexts, their device buffers and pinned frame buffers kept between calls. */
+typedef struct NcrFramePool NcrFramePool;
+NcrFramePool* NcrCreateFramePool(long width, long height, int alpha, int n_workers);   /* NULL without a usable device */
+void NcrDestroyFramePool(NcrFramePool* pool);
+int NcrFramePoolWorkers(NcrFramePool* pool);
+long NcrFramePoolRender(NcrFramePool* pool, const void* const* traces, const long* trace_bytes, long n_frames,
+                        Texture* const* textures, long n_textures, int present, NcrFrameSink sink, void* user);
 long NcrYUV420PSize(RenderContext* ctx);
 long NcrGetBufferAsYUV420P(RenderContext* ctx, unsigned char* out);
 

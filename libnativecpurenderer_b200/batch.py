@@ -1,4 +1,4 @@
-"""Frame-parallel batch render: Python face of ``NcrRenderFrames`` (include/ncr_b200.h).
+"""Frame-parallel batch render: Python face of ``NcrFramePool*`` / ``NcrRenderFrames`` (include/ncr_b200.h).
 
 The reference sketches this as ``MultiThreadedVideoRenderContextPreparer`` (reference
 src/libNativeCPURendererPybind.py:302-367: record the calls of N frames, replay them on a block of contexts) and leaves
@@ -14,20 +14,22 @@ import numpy as np
 from . import trace as _trace
 
 _SINK = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_long, ctypes.POINTER(ctypes.c_ubyte), ctypes.c_long)
+_PRESENT = {"u8": 0, "yuv420p": 1}
 
 
-def render_frames(renderer, width: int, height: int, alpha: bool, traces: Sequence[np.ndarray], textures: Iterable,
-                  on_frame: Callable[[int, np.ndarray], None] | None = None, workers: int = 8, present: str = "u8") -> int:
-    """Render ``traces`` (one recorded frame each; every frame must start with ``set_color``) on ``workers`` contexts.
+def _declare(lib) -> None:
+    if getattr(lib, "_ncr_batch_declared", False):
+        return
+    P, L, I = ctypes.c_void_p, ctypes.c_long, ctypes.c_int
+    lib.NcrCreateFramePool.restype, lib.NcrCreateFramePool.argtypes = P, (L, L, I, I)
+    lib.NcrDestroyFramePool.restype, lib.NcrDestroyFramePool.argtypes = None, (P,)
+    lib.NcrFramePoolWorkers.restype, lib.NcrFramePoolWorkers.argtypes = I, (P,)
+    lib.NcrFramePoolRender.restype, lib.NcrFramePoolRender.argtypes = L, (P, P, P, L, P, L, I, _SINK, P)
+    lib.NcrRenderFrames.restype, lib.NcrRenderFrames.argtypes = L, (L, L, I, P, P, L, P, L, I, I, _SINK, P)
+    lib._ncr_batch_declared = True
 
-    ``on_frame(index, pixels)`` is called in frame order with a uint8 view that is only valid during the call (copy it to
-    keep it).  ``present`` is "u8" (the ``GetBufferAsUInt8`` image) or "yuv420p" (``NcrGetBufferAsYUV420P`` planes).
-    Returns the number of frames rendered; raises on device errors or frames that are not independent."""
-    lib = renderer.lib
-    fn = lib.NcrRenderFrames
-    fn.restype = ctypes.c_long
-    fn.argtypes = (ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p,
-                   ctypes.c_long, ctypes.c_int, ctypes.c_int, _SINK, ctypes.c_void_p)
+
+def _call(renderer, traces: Sequence[np.ndarray], textures, on_frame, invoke) -> int:
     textures = list(textures)
     n = len(traces)
     ptrs = (ctypes.c_void_p * max(n, 1))(*[t.ctypes.data for t in traces])
@@ -43,12 +45,58 @@ def render_frames(renderer, width: int, height: int, alpha: bool, traces: Sequen
         except BaseException as e:   # never unwind through the C frames
             err.append(e)
 
-    cb = _SINK(_sink)
-    rc = fn(width, height, int(alpha), ptrs, sizes, n, table, len(textures), workers, {"u8": 0, "yuv420p": 1}[present], cb, None)
+    rc = invoke(ptrs, sizes, n, table, len(textures), _SINK(_sink))
     if err:
         raise err[0]
     if rc == -2:
         raise ValueError("a frame does not start by overwriting the canvas (set_color): frames would not be independent")
     if rc < 0:
-        raise RuntimeError(f"NcrRenderFrames failed: {renderer.last_error()}")
+        raise RuntimeError(f"batch render failed: {renderer.last_error()}")
     return int(rc)
+
+
+class FramePool:
+    """``workers`` render contexts (one CUDA stream each) with their device and pinned buffers, kept between renders."""
+
+    def __init__(self, renderer, width: int, height: int, alpha: bool, workers: int = 8):
+        _declare(renderer.lib)
+        self._r = renderer
+        self._p = renderer.lib.NcrCreateFramePool(width, height, int(alpha), workers)
+        if not self._p:
+            raise RuntimeError(f"NcrCreateFramePool failed: {renderer.last_error()}")
+        self.workers = renderer.lib.NcrFramePoolWorkers(self._p)
+
+    def render(self, traces: Sequence[np.ndarray], textures: Iterable,
+               on_frame: Callable[[int, np.ndarray], None] | None = None, present: str = "u8") -> int:
+        """``on_frame(index, pixels)`` runs in frame order with a uint8 view valid only during the call."""
+        lib, p, mode = self._r.lib, self._p, _PRESENT[present]
+        return _call(self._r, traces, textures, on_frame,
+                     lambda ptrs, sizes, n, table, nt, cb: lib.NcrFramePoolRender(p, ptrs, sizes, n, table, nt, mode, cb, None))
+
+    def close(self) -> None:
+        if self._p:
+            self._r.lib.NcrDestroyFramePool(self._p)
+            self._p = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def render_frames(renderer, width: int, height: int, alpha: bool, traces: Sequence[np.ndarray], textures: Iterable,
+                  on_frame: Callable[[int, np.ndarray], None] | None = None, workers: int = 8, present: str = "u8") -> int:
+    """One-shot: render ``traces`` (one recorded frame each; every frame must start with ``set_color``) on ``workers``
+    contexts created for this call.  ``present`` is "u8" (``GetBufferAsUInt8`` image) or "yuv420p" (planes)."""
+    _declare(renderer.lib)
+    lib, mode = renderer.lib, _PRESENT[present]
+    return _call(renderer, traces, textures, on_frame,
+                 lambda ptrs, sizes, n, table, nt, cb: lib.NcrRenderFrames(width, height, int(alpha), ptrs, sizes, n, table, nt,
+                                                                           workers, mode, cb, None))

@@ -56,14 +56,56 @@ void reset_state(RenderContext* ctx) {
 
 }   // namespace
 
-extern "C" long NcrRenderFrames(long width, long height, int alpha, const void* const* traces, const long* trace_bytes,
-                                long n_frames, Texture* const* textures, long n_textures, int n_workers, int present,
-                                NcrFrameSink sink, void* user) {
+struct NcrFramePool {
+    long width = 0, height = 0;
+    int alpha = 0;
+    std::vector<RenderContext*> ctx;
+    std::vector<unsigned char*> buf;   // pinned, large enough for either present mode
+    long u8_bytes = 0, yuv_bytes = 0;
+};
+
+extern "C" {
+
+// Contexts, their device buffers and the pinned frame buffers are created once and reused by every render call
+// (cudaMalloc / cudaFree synchronise the device: they must not sit inside a render).
+NcrFramePool* NcrCreateFramePool(long width, long height, int alpha, int n_workers) {
+    if (width <= 0 || height <= 0) return nullptr;
+    n_workers = std::max(1, std::min(n_workers, 64));
+    NcrFramePool* p = new NcrFramePool();
+    p->width = width; p->height = height; p->alpha = alpha;
+    for (int k = 0; k < n_workers; ++k) {
+        RenderContext* c = CreateRenderContext(width, height, alpha != 0);
+        if (!c) break;
+        p->u8_bytes = GetBufferSize(c);
+        p->yuv_bytes = NcrYUV420PSize(c);
+        unsigned char* b = (unsigned char*)NcrAllocHost((unsigned long long)std::max(p->u8_bytes, p->yuv_bytes));
+        if (!b) { DestroyRenderContext(c); break; }
+        p->ctx.push_back(c);
+        p->buf.push_back(b);
+    }
+    if (p->ctx.empty()) { delete p; return nullptr; }
+    return p;
+}
+
+void NcrDestroyFramePool(NcrFramePool* p) {
+    if (!p) return;
+    for (size_t k = 0; k < p->ctx.size(); ++k) {
+        NcrFreeHost(p->buf[k]);
+        DestroyRenderContext(p->ctx[k]);
+    }
+    delete p;
+}
+
+int NcrFramePoolWorkers(NcrFramePool* p) { return p ? (int)p->ctx.size() : 0; }
+
+long NcrFramePoolRender(NcrFramePool* p, const void* const* traces, const long* trace_bytes, long n_frames,
+                        Texture* const* textures, long n_textures, int present, NcrFrameSink sink, void* user) {
     if (n_frames <= 0) return 0;
-    if (!traces || !trace_bytes || width <= 0 || height <= 0 || (present != 0 && present != 1)) return -1;
+    if (!p || !traces || !trace_bytes || (present != 0 && present != 1)) return -1;
     for (long f = 0; f < n_frames; ++f)
         if (!traces[f] || trace_bytes[f] <= 0 || !frame_is_independent((const unsigned char*)traces[f], trace_bytes[f])) return -2;
-    n_workers = (int)std::max<long>(1, std::min<long>(std::min<long>(n_workers, 64), n_frames));
+    const int n_workers = (int)std::min<long>((long)p->ctx.size(), n_frames);
+    const long bytes = present == 1 ? p->yuv_bytes : p->u8_bytes;
 
     std::mutex m;
     std::condition_variable cv;
@@ -76,11 +118,8 @@ extern "C" long NcrRenderFrames(long width, long height, int alpha, const void* 
     };
 
     auto worker = [&](int k) {
-        RenderContext* ctx = CreateRenderContext(width, height, alpha != 0);
-        if (!ctx) { fail(); return; }
-        const long bytes = present == 1 ? NcrYUV420PSize(ctx) : GetBufferSize(ctx);
-        unsigned char* buf = (unsigned char*)NcrAllocHost((unsigned long long)bytes);   // pinned: the readback is a direct DMA
-        if (!buf) { DestroyRenderContext(ctx); fail(); return; }
+        RenderContext* ctx = p->ctx[k];
+        unsigned char* buf = p->buf[k];
         for (long f = k; f < n_frames; f += n_workers) {
             {
                 std::lock_guard<std::mutex> g(m);
@@ -101,8 +140,6 @@ extern "C" long NcrRenderFrames(long width, long height, int alpha, const void* 
             next = f + 1;
             cv.notify_all();
         }
-        NcrFreeHost(buf);
-        DestroyRenderContext(ctx);
     };
 
     std::vector<std::thread> pool;
@@ -110,3 +147,19 @@ extern "C" long NcrRenderFrames(long width, long height, int alpha, const void* 
     for (auto& t : pool) t.join();
     return failed ? -1 : n_frames;
 }
+
+// One-shot convenience: pool for this call only.
+long NcrRenderFrames(long width, long height, int alpha, const void* const* traces, const long* trace_bytes, long n_frames,
+                     Texture* const* textures, long n_textures, int n_workers, int present, NcrFrameSink sink, void* user) {
+    if (n_frames <= 0) return 0;
+    if (!traces || !trace_bytes || width <= 0 || height <= 0 || (present != 0 && present != 1)) return -1;
+    for (long f = 0; f < n_frames; ++f)
+        if (!traces[f] || trace_bytes[f] <= 0 || !frame_is_independent((const unsigned char*)traces[f], trace_bytes[f])) return -2;
+    NcrFramePool* p = NcrCreateFramePool(width, height, alpha, (int)std::min<long>(n_workers, n_frames));
+    if (!p) return -1;
+    const long rc = NcrFramePoolRender(p, traces, trace_bytes, n_frames, textures, n_textures, present, sink, user);
+    NcrDestroyFramePool(p);
+    return rc;
+}
+
+}   // extern "C"

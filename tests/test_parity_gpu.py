@@ -483,6 +483,11 @@ def test_batch_render_delivers_every_frame_in_order(present, gpu, port):
     assert batch.render_frames(gpu, w, h, False, traces, tex, on_frame=lambda i, px: got.append((i, px.tobytes())),
                                workers=3, present=present) == 13
     assert [i for i, _ in got] == list(range(13))
+    with batch.FramePool(gpu, w, h, False, workers=4) as pool:   # a kept pool gives the same frames, call after call
+        for _ in range(2):
+            again = []
+            assert pool.render(traces, tex, on_frame=lambda i, px: again.append((i, px.tobytes())), present=present) == 13
+            assert again == got
     ptex = [port.Texture.from_numpy(t) for t in tex_np]
     for R, T in ((gpu, tex), (port, ptex)):
         for f in (0, 5, 12):
