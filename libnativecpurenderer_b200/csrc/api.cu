@@ -16,6 +16,8 @@
 #include <atomic>
 #include <memory>
 #include <mutex>
+#include <thread>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/ncr_b200.h"
@@ -53,7 +55,13 @@ bool ck(cudaError_t e, const char* what) {
 #define CK(call) ck((call), #call)
 
 // Selects the device once (NCR_DEVICE, else LOCAL_RANK, else 0) and makes it current on the calling thread.
+std::mutex g_init_mu;
+std::atomic<int> g_init_done{0};   // published copy of g_init for the lock-free fast path
+
 bool use_device() {
+    if (g_init_done.load(std::memory_order_acquire) == 1) return cudaSetDevice(g_dev) == cudaSuccess;
+    std::lock_guard<std::mutex> init_lock(g_init_mu);   // first use from several threads at once (frame pool, tests)
+    struct Publish { ~Publish() { g_init_done.store(g_init, std::memory_order_release); } } publish;
     if (g_init == 1) return cudaSetDevice(g_dev) == cudaSuccess;
     if (g_init == -1) return false;
     int want = 0;
@@ -1073,13 +1081,28 @@ Texture* CreateMilthmHitEffectTexture(Texture* mask_, double seed, double t, dou
     // cpp:1426-1436 indexes mask and output as [i*height*4 + j*4] (i over width): linear element i*h + j.
     std::vector<double> out(n * 4);
     bool bytes_exact = true;
-    for (i64 i = 0; i < w; ++i) {
-        for (i64 j = 0; j < h; ++j) {
-            const double av = ncr_hit_effect_alpha(seed, t, (double)i / w, (double)j / h);
-            const size_t k = (size_t)i * h + j;
-            out[4 * k + 0] = r; out[4 * k + 1] = g; out[4 * k + 2] = b;
-            out[4 * k + 3] = av * mask_a[k];
+    // Texels are independent, so the rows are spread over the host cores (milrenderer builds 480 of these 512^2 textures at
+    // start-up, mil:856-860: ~58 s on one core); every texel runs the same scalar libm code, so the result stays bit-identical.
+    auto rows = [&](i64 i0, i64 i1) {
+        for (i64 i = i0; i < i1; ++i) {
+            for (i64 j = 0; j < h; ++j) {
+                const double av = ncr_hit_effect_alpha(seed, t, (double)i / w, (double)j / h);
+                const size_t k = (size_t)i * h + j;
+                out[4 * k + 0] = r; out[4 * k + 1] = g; out[4 * k + 2] = b;
+                out[4 * k + 3] = av * mask_a[k];
+            }
         }
+    };
+    unsigned n_thr = std::thread::hardware_concurrency();
+    if (const char* e = getenv("NCR_HOST_THREADS")) n_thr = (unsigned)atoi(e);
+    n_thr = std::max(1u, std::min({n_thr, 32u, (unsigned)std::max<i64>(1, w / 8)}));
+    if (n < (size_t)1 << 14) n_thr = 1;
+    if (n_thr == 1) {
+        rows(0, w);
+    } else {
+        std::vector<std::thread> pool;
+        for (unsigned k = 0; k < n_thr; ++k) pool.emplace_back(rows, w * k / n_thr, w * (k + 1) / n_thr);
+        for (auto& th : pool) th.join();
     }
     // Store as RGBA8 when every element is exactly some k/255.0 (true for milrenderer's call, pyb:45-47).
     unsigned char rgb8[3];

@@ -103,6 +103,37 @@ __global__ void __launch_bounds__(256) ncr_bin_fine(NcrFlushArgs A) {
         if (lane == 0) { A.fine_off[tile] = 0; A.fine_off[n_tiles + tile] = 0; }
         return;
     }
+    if (ccount <= 128) {
+        // Short bin list (the common case of chart-like frames): one step holds every candidate in registers, so the list is
+        // read once — count, allocate, write, without the second scan.
+        uint32_t idx[4], m[4];
+        bool hit[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) idx[u] = A.coarse_list[cbase + min(u * 32 + lane, ccount - 1)];   // clamped, unconditional
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const NcrBox b = A.boxes[idx[u]];
+            hit[u] = box_hits(b, x0, y0, x1, y1) && (u * 32 + lane < ccount);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { m[u] = __ballot_sync(0xffffffffu, hit[u]); count += __popc(m[u]); }
+        uint32_t off = 0;
+        if (lane == 0) {
+            off = count ? atomicAdd(&A.cursors[1], count) : 0u;
+            if (off + count > A.fine_cap) { count = 0; atomicExch(&A.cursors[4], 2u); }
+            A.fine_off[tile] = off;
+            A.fine_off[n_tiles + tile] = count;
+        }
+        off = __shfl_sync(0xffffffffu, off, 0);
+        count = __shfl_sync(0xffffffffu, count, 0);
+        if (count == 0) return;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (hit[u]) A.fine_list[off + __popc(m[u] & ((1u << lane) - 1))] = idx[u];
+            off += __popc(m[u]);
+        }
+        return;
+    }
     for (uint32_t k = 0; k < ccount; k += 128) {
         uint32_t idx[4];
         bool hit[4];
