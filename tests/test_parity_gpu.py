@@ -502,3 +502,50 @@ def _replay_calls(ctx, arr, textures, R):
     from conftest import REPLAY_LIB
 
     trace.Replayer(REPLAY_LIB, R.path).run(ctx, arr, textures)
+
+
+def test_8k_canvas_matches_port(gpu, port, image_rgba):
+    """Maximum-size end of the path: a 7680x4320 RGB canvas (796 MB of f64 on the device, 129,600 tiles) with one draw of
+    every kind, bit-exact against the C restatement."""
+    w, h = 7680, 4320
+    got = []
+    for R in (gpu, port):
+        ctx = R.RenderContext(w, h, False)
+        tex = R.Texture.from_numpy(image_rgba)
+        ctx.set_color(.2, .3, .4, 1)
+        ctx.save_state()
+        ctx.translate(w * .5, h * .5)
+        ctx.rotate(.3)
+        ctx.scale(20, 12)
+        ctx.apply_color_transform(1, .9, .8, .7)
+        ctx.draw_texture(tex, -64, -64, 128, 128)
+        ctx.draw_splitted_texture(tex, 70, -64, 128, 128, .1, .9, .2, .8)
+        ctx.restore_state()
+        ctx.draw_rect(7000.5, 4000.5, 900, 900, 1, 0, 0, .5)          # clipped by the right/bottom edges
+        ctx.draw_vertical_grd(0, 0, w, 400, 0, 0, 0, .8, 0, 0, 0, 0.0)
+        ctx.draw_circle(1000, 3000, 700, 0, 1, 0, .4)
+        ctx.draw_line(100, 4200, 7600, 100, 9, 1, 1, 1, .9)
+        img = ctx.get_buffer_as_uint8()
+        got.append(hashlib.sha1(bytes(img)).hexdigest())
+        del ctx
+    assert got[0] == got[1]
+
+
+def test_100k_tiny_draws_one_flush(gpu, port):
+    """Command-count end of the path: 100,000 small rects and circles in ONE flush (tile-list capacity is sized from the
+    recorded boxes), bit-exact against the C restatement, u8 and f64."""
+    import random
+
+    got = []
+    for R in (gpu, port):
+        ctx = R.RenderContext(640, 360, True)
+        ctx.set_color(0, 0, 0, 1)
+        rng = random.Random(11)
+        for k in range(100000):
+            x, y = rng.uniform(-5, 645), rng.uniform(-5, 365)
+            if k % 7:
+                ctx.draw_rect(x, y, rng.uniform(.5, 6), rng.uniform(.5, 6), rng.random(), rng.random(), rng.random(), rng.uniform(.1, 1))
+            else:
+                ctx.draw_circle(x, y, rng.uniform(.5, 4), rng.random(), rng.random(), rng.random(), rng.uniform(.1, 1))
+        got.append(cases.digest(ctx))
+    assert got[0] == got[1]
