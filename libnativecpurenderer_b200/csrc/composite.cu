@@ -262,6 +262,45 @@ __device__ __forceinline__ void shade_rgba8(const NcrCmd& c, uint32_t lut_base, 
     }
 }
 
+// Bilinear extension (parity unpinned, cpp:575-620 formula) on RGBA8 textures, written like the nearest path: straight-line
+// over the four pixel slots, the sixteen texel loads issued back to back, decode through the lane-private table.  Performs
+// exactly the operations of sample_slow() + the caller's colour transform and blend, in the same order.
+template <bool ALPHA, bool COUNT>
+__device__ __forceinline__ void shade_bilinear_rgba8(const NcrCmd& c, uint32_t lut_base, int tw, int th, const double (&u)[NCR_P],
+                                                     const double (&v)[NCR_P], const bool (&in)[NCR_P], double (&dr)[NCR_P],
+                                                     double (&dg)[NCR_P], double (&db)[NCR_P], double (&da)[NCR_P],
+                                                     unsigned long long& n_applied) {
+    const uint32_t* t32 = (const uint32_t*)c.tex;
+    uint32_t t[NCR_P][4];
+    double fu[NCR_P], fv[NCR_P];
+    FOR4 {
+        double uu = u[p], vv = v[p];
+        clamp_uv(uu, vv, tw, th);
+        int xi = __double2int_rz(uu), yi = __double2int_rz(vv);
+        xi = min(max(xi, 0), tw - 1);   // memory safety only; no-op for defined inputs
+        yi = min(max(yi, 0), th - 1);
+        const int dx = xi + 1 < tw ? 1 : 0, dy = yi + 1 < th ? tw : 0;
+        const int idx = yi * tw + xi;
+        t[p][0] = in[p] ? __ldg(t32 + idx) : 0u;
+        t[p][1] = in[p] ? __ldg(t32 + idx + dx) : 0u;
+        t[p][2] = in[p] ? __ldg(t32 + idx + dy) : 0u;
+        t[p][3] = in[p] ? __ldg(t32 + idx + dy + dx) : 0u;
+        fu[p] = SUB(uu, (double)xi);
+        fv[p] = SUB(vv, (double)yi);
+    }
+    const double ct0 = c.ct[0], ct1 = c.ct[1], ct2 = c.ct[2], ct3 = c.ct[3];
+    FOR4 {
+        const double mu = SUB(1.0, fu[p]), mv = SUB(1.0, fv[p]);
+#define NCR_TAP(K) ADD(ADD(ADD(MUL(MUL(lut_byte<K>(lut_base, t[p][0]), mu), mv), MUL(MUL(lut_byte<K>(lut_base, t[p][1]), fu[p]), mv)), \
+                           MUL(MUL(lut_byte<K>(lut_base, t[p][2]), mu), fv[p])), MUL(MUL(lut_byte<K>(lut_base, t[p][3]), fu[p]), fv[p]))
+        const double r = MUL(NCR_TAP(0), ct0), g = MUL(NCR_TAP(1), ct1), b = MUL(NCR_TAP(2), ct2), a = MUL(NCR_TAP(3), ct3);
+#undef NCR_TAP
+        const bool opq = blend<ALPHA>(dr[p], dg[p], db[p], da[p], r, g, b, a, in[p]);
+        store_opaque(dr[p], dg[p], db[p], r, g, b, opq);
+        if (COUNT) n_applied += in[p] ? 1 : 0;
+    }
+}
+
 // Fast path of the two hot ops — DrawTexture (inverse-mapped, cpp:753-778) and DrawSplittedTexture (cpp:781-820) on
 // RGBA8 textures with nearest sampling.  Written as straight-line code over the four pixel slots (no branch between
 // slots), so the f64 dependency chains of the slots interleave.
@@ -484,6 +523,9 @@ __device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A
             tx[p] = in[p] ? __ldg(t32 + (yi * tw + xi)) : 0u;
         }
         shade_rgba8<ALPHA, COUNT, false>(c, lut_base, tx, in, dr, dg, db, da, n_applied);   // r * 1.0 is exact: one code copy
+    } else if ((flags & (NCR_F_BILINEAR | NCR_F_TEX_ALPHA | NCR_F_TEX_F64)) == (NCR_F_BILINEAR | NCR_F_TEX_ALPHA) &&
+               (unsigned long long)tw * (unsigned long long)th < (1ull << 31)) {
+        if (__any_sync(FULL, any_slot(in))) shade_bilinear_rgba8<ALPHA, COUNT>(c, lut_base, tw, th, u, v, in, dr, dg, db, da, n_applied);
     } else {
         FOR4 if (in[p]) {
             double s[4];
