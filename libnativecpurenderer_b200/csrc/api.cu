@@ -14,6 +14,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sched.h>
+#include <time.h>
+#include <chrono>
 #include <atomic>
 #include <memory>
 #include <mutex>
@@ -291,9 +293,9 @@ void harvest(NcrContext* c) {
 
 // How a host thread waits for its context's stream (NCR_SYNC=spin|yield|block|auto, default auto).
 //   spin   cudaStreamSynchronize: the driver spins — lowest latency, one core burnt per waiting context;
-//   yield  poll a stream event and sched_yield() between polls: the core goes to any runnable thread (a sibling context
-//          still recording its frame) and comes back at once when there is none — lets a frame-parallel render run more
-//          contexts than it has cores (measured: 8 contexts on 4 cores reach the GPU-bound rate, 4 spinning ones do not);
+//   yield  poll a stream event: sched_yield() between polls for ~150 us, then 80 us naps — the core goes to a sibling context
+//          that is still recording its frame; lets a frame-parallel render run more contexts than it has cores (measured:
+//          8 contexts on 4 cores reach the GPU-bound rate, 4 spinning ones do not);
 //   block  event with cudaEventBlockingSync: the thread sleeps; costs ~40 % on sub-millisecond frames (wake-up latency);
 //   auto   yield while this process has more live contexts than its share of the cores (affinity mask / LOCAL_WORLD_SIZE),
 //          else spin.
@@ -332,7 +334,20 @@ bool sync_ctx(NcrContext* c) {
     } else if (sync_mode() == 2 && c->ev_sync) {
         ok = CK(cudaEventRecord(c->ev_sync, c->stream));
         cudaError_t q = cudaSuccess;
-        while (ok && (q = cudaEventQuery(c->ev_sync)) == cudaErrorNotReady) sched_yield();   // give the core to a recording thread
+        // Poll: yield the core for the first ~150 us (sub-millisecond frames finish inside this window with no wake-up
+        // latency), then sleep between polls so that long waits leave the core to threads that are recording frames —
+        // under CFS a yielding poller still takes its fair share of the core from them.
+        const auto t0 = std::chrono::steady_clock::now();
+        bool nap = false;
+        while (ok && (q = cudaEventQuery(c->ev_sync)) == cudaErrorNotReady) {
+            if (!nap) {
+                sched_yield();
+                nap = std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(150);
+            } else {
+                struct timespec ts = {0, 80 * 1000};
+                nanosleep(&ts, nullptr);
+            }
+        }
         if (ok && q != cudaSuccess) ok = CK(q);
     } else {
         ok = CK(cudaStreamSynchronize(c->stream));
