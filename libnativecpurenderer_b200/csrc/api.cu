@@ -211,6 +211,7 @@ struct NcrContext {
     DevVec<unsigned char> d_u8;
     DevVec<unsigned char> d_yuv;
     bool u8_valid = false;
+    bool yuv_valid = false;   // d_yuv holds the planes of the current canvas
     uint32_t* h_cursors = nullptr;   // pinned, 8 words
     bool cursors_pending = false;
     cudaStream_t stream = nullptr;
@@ -266,6 +267,7 @@ bool alloc_canvas(NcrContext* c, i64 w, i64 h) {
     c->w = w;
     c->h = h;
     c->u8_valid = false;
+    c->yuv_valid = false;
     c->has_last = false;
     return true;
 }
@@ -361,17 +363,31 @@ bool sync_ctx(NcrContext* c) {
     return !c->failed;
 }
 
-// Submits the recorded batch.  want_u8: also produce the (iu8)(v*255) image in d_u8 (fused into the composite).
-bool flush(NcrContext* c, bool want_u8) {
+size_t yuv_bytes_of(const NcrContext* c) {
+    return (size_t)c->w * c->h + 2 * (size_t)((c->w + 1) / 2) * (size_t)((c->h + 1) / 2);
+}
+
+// Submits the recorded batch.  want_u8: also produce the (iu8)(v*255) image in d_u8; want_yuv: the YUV 4:2:0 planes of that
+// image in d_yuv (both fused into the composite's tile write-back).  With nothing pending, the outputs that are not
+// already current are produced from the canvas by the standalone kernels.
+bool flush(NcrContext* c, bool want_u8, bool want_yuv = false) {
     if (!use_device()) return false;
     const size_t n_elems = (size_t)c->w * c->h * ipp_of(c);
     if (c->n == 0) {
-        if (want_u8 && !c->u8_valid && n_elems) {
+        const bool need_yuv = want_yuv && !c->yuv_valid && n_elems;
+        if ((want_u8 || need_yuv) && !c->u8_valid && n_elems) {
             if (!c->d_u8.reserve(n_elems)) return false;
             ncr_launch_convert_u8((const double*)c->fb->p, c->d_u8.p, n_elems, c->stream);
             g_launches += 1;
             c->stats.kernel_launches += 1;
             c->u8_valid = true;
+        }
+        if (need_yuv) {
+            if (!c->d_yuv.reserve(yuv_bytes_of(c))) return false;
+            ncr_launch_yuv420p(c->d_u8.p, c->d_yuv.p, (int)c->w, (int)c->h, ipp_of(c), c->stream);
+            g_launches += 1;
+            c->stats.kernel_launches += 1;
+            c->yuv_valid = true;
         }
         return true;
     }
@@ -388,6 +404,7 @@ bool flush(NcrContext* c, bool want_u8) {
               c->d_coarse.reserve(c->coarse_need + 1) && c->d_coarse_off.reserve(2 * n_bins) &&
               c->d_fine.reserve(c->fine_need + 1) && c->d_fine_off.reserve(2 * n_tiles) && c->d_cursors.reserve(8);
     if (ok && want_u8) ok = c->d_u8.reserve(n_elems);
+    if (ok && want_yuv) ok = c->d_yuv.reserve(yuv_bytes_of(c));
     if (!ok) { c->failed = true; return false; }
     ok = CK(cudaMemcpyAsync(c->d_cmds.p, S.cmds.p, c->n * sizeof(NcrCmd), cudaMemcpyHostToDevice, c->stream)) &&
          CK(cudaMemcpyAsync(c->d_boxes.p, S.boxes.p, c->n * sizeof(NcrBox), cudaMemcpyHostToDevice, c->stream));
@@ -400,6 +417,7 @@ bool flush(NcrContext* c, bool want_u8) {
 
     A.fb = (double*)c->fb->p;
     A.u8_out = want_u8 ? c->d_u8.p : nullptr;
+    A.yuv_out = want_yuv ? c->d_yuv.p : nullptr;
     A.cmds = c->d_cmds.p;
     A.boxes = c->d_boxes.p;
     A.aux = c->d_aux.p;
@@ -433,6 +451,7 @@ bool flush(NcrContext* c, bool want_u8) {
     c->coarse_need = c->fine_need = 0;
     c->load_fb = true;
     c->u8_valid = want_u8;
+    c->yuv_valid = want_yuv;
     c->cur ^= 1;
     return true;
 }
@@ -686,17 +705,14 @@ long NcrYUV420PSize(RenderContext* ctx) {
     return (long)(c->w * c->h + 2 * ((c->w + 1) / 2) * ((c->h + 1) / 2));
 }
 
-// Present path: flush with the fused u8 image, convert it to planar YUV 4:2:0 on the same stream, read back 1.5 B/px.
+// Present path: the composite writes the YUV 4:2:0 planes of the (iu8)(v*255) image with its tiles (a standalone kernel does
+// it when nothing is pending); only the planes, 1.5 B/px, are read back.
 long NcrGetBufferAsYUV420P(RenderContext* ctx, unsigned char* out) {
     NcrContext* c = live(ctx);
     if (!c || !out) return -1;
     const long bytes = NcrYUV420PSize(ctx);
     if (bytes <= 0) return 0;
-    if (!flush(c, true)) return -1;
-    if (!c->d_yuv.reserve((size_t)bytes)) { c->failed = true; return -1; }
-    ncr_launch_yuv420p(c->d_u8.p, c->d_yuv.p, (int)c->w, (int)c->h, ipp_of(c), c->stream);
-    g_launches += 1;
-    c->stats.kernel_launches += 1;
+    if (!flush(c, false, true)) return -1;
     if (!CK(cudaGetLastError()) ||
         !CK(cudaMemcpyAsync(out, c->d_yuv.p, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream))) { c->failed = true; return -1; }
     c->stats.d2h_bytes += (size_t)bytes;
@@ -1267,6 +1283,7 @@ int NcrRerunLastFlush(RenderContext* ctx, int iters, int flush_l2, float* ms_out
         }
     }
     c->u8_valid = c->last.u8_out != nullptr;
+    c->yuv_valid = c->last.yuv_out != nullptr;
     return 0;
 }
 

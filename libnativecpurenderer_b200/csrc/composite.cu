@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, NCR_COMPOSITE_MIN_CTAS)
         const int tile = task / NCR_TASKS_PER_TILE, sub = task % NCR_TASKS_PER_TILE;
         const uint32_t loff = __ldg(&A.fine_off[tile]);
         const uint32_t lcount = __ldg(&A.fine_off[n_tiles + tile]);
-        if (lcount == 0 && A.u8_out == nullptr) continue;
+        if (lcount == 0 && A.u8_out == nullptr && A.yuv_out == nullptr) continue;
 
         const int x0 = (tile % A.d.tiles_x) * NCR_TILE + (sub % (16 / NCR_RW)) * NCR_RW;
         const int y0 = (tile / A.d.tiles_x) * NCR_TILE + (sub / (16 / NCR_RW)) * NCR_RH;
@@ -664,6 +664,33 @@ __global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, NCR_COMPOSITE_MIN_CTAS)
                 } else {
                     unsigned char* o = A.u8_out + pix;
                     o[0] = ncr_to_u8(dr[p]); o[1] = ncr_to_u8(dg[p]); o[2] = ncr_to_u8(db[p]);
+                }
+            }
+        }
+        // Present path, fused: the YUV 4:2:0 planes of the (iu8)(v*255) image, same arithmetic as ncr_yuv420p
+        // (kernels.cu).  A 2x2 chroma block is (lane, lane^1) x (lane, lane^8) of the same pixel slot — region origins are
+        // even — so the block sums are two shuffles of the packed 10-bit channel sums; a missing neighbour column / row
+        // (odd canvas size) is replaced by the pixel's own, which is the edge replication of the standalone kernel.
+        if (A.yuv_out) {   // warp-uniform
+            const int cw = (W + 1) >> 1, chh = (H + 1) >> 1;
+            unsigned char* const Yp = A.yuv_out;
+            unsigned char* const Up = Yp + (size_t)W * H;
+            unsigned char* const Vp = Up + (size_t)cw * chh;
+            FOR4 {
+                const int x = S.xs[SX(p)], y = S.ys[SY(p)];
+                const int r = ncr_to_u8(dr[p]), g = ncr_to_u8(dg[p]), b = ncr_to_u8(db[p]);
+                if (valid[p]) Yp[(size_t)y * W + x] = (unsigned char)(((66 * r + 129 * g + 25 * b + 128) >> 8) + 16);
+                const uint32_t pk = (uint32_t)r | ((uint32_t)g << 10) | ((uint32_t)b << 20);
+                const uint32_t side = __shfl_xor_sync(FULL, pk, 1);
+                const uint32_t row = pk + (((x ^ 1) < W) ? side : pk);
+                const uint32_t other = __shfl_xor_sync(FULL, row, 8);
+                const uint32_t sum = row + (((y ^ 1) < H) ? other : row);
+                if (valid[p] && !((x | y) & 1)) {
+                    const int mr = (int)((sum & 1023u) + 2u) >> 2, mg = (int)(((sum >> 10) & 1023u) + 2u) >> 2,
+                              mb = (int)((sum >> 20) + 2u) >> 2;
+                    const size_t ci = (size_t)(y >> 1) * cw + (x >> 1);
+                    Up[ci] = (unsigned char)(((-38 * mr - 74 * mg + 112 * mb + 128) >> 8) + 128);
+                    Vp[ci] = (unsigned char)(((112 * mr - 94 * mg - 18 * mb + 128) >> 8) + 128);
                 }
             }
         }

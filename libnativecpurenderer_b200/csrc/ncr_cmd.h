@@ -76,6 +76,7 @@ struct NcrFlushArgs {
     NcrFrameDims d;
     double* fb;                 // canonical f64 canvas [h][w][ipp]
     unsigned char* u8_out;      // fused (iu8)(v*255) image, or nullptr
+    unsigned char* yuv_out;     // fused YUV 4:2:0 planes of that image (present path), or nullptr
     const NcrCmd* cmds;
     const NcrBox* boxes;
     const double* aux;

@@ -418,9 +418,14 @@ def test_yuv420p_present_matches_port_parity_unpinned(shape, gpu, port, image_rg
         ctx = R.RenderContext(w, h, alpha)
         tex = cases.tiny_textures(R, image_rgba)
         streams.stream_random(ctx, tex, 77, n=60)
-        yuv = ctx.get_buffer_as_yuv420p()
+        yuv = ctx.get_buffer_as_yuv420p()          # draws pending: planes come fused out of the composite
         assert yuv.size == w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2)
-        got.append((yuv.tobytes(), cases.digest(ctx)))
+        again = ctx.get_buffer_as_yuv420p()        # nothing pending, planes still current: just a copy
+        ctx.fill_color(.3, .6, .9, .25)
+        ctx.get_buffer_as_uint8()                  # flush without the planes ...
+        alone = ctx.get_buffer_as_yuv420p()        # ... so these come from the standalone kernel
+        got.append((yuv.tobytes(), again.tobytes(), alone.tobytes(), cases.digest(ctx)))
+        assert got[-1][0] == got[-1][1] and got[-1][0] != got[-1][2]
     assert got[0] == got[1]
 
 
