@@ -26,7 +26,13 @@ __device__ __forceinline__ bool box_hits(const NcrBox& bx, int x0, int y0, int x
 // hits (ballot + popc, four independent box loads in flight per lane), one block-level prefix gives every warp its write
 // position, and the warps re-scan their segments writing command indices in submission order.  No barrier inside the
 // loops.  Lists of different bins are carved out of one array with a single atomicAdd per bin.
-__global__ void __launch_bounds__(256) ncr_bin_coarse(NcrFlushArgs A) {
+// use_masks != 0: the hit ballots of the counting scan are kept in shared memory (one word per 32 commands per warp,
+// `mask_words` words per warp) and the writing scan replays them instead of loading every box a second time — the scan
+// is L2-bandwidth bound (bins x commands x 16 B per pass), so this halves its traffic.  The host enables it whenever the
+// masks fit (n_cmds / 8 bits per CTA).
+extern __shared__ uint32_t ncr_coarse_masks[];
+
+__global__ void __launch_bounds__(256) ncr_bin_coarse(NcrFlushArgs A, int use_masks, uint32_t mask_words) {
     const int bin = blockIdx.x;
     const int n_bins = A.d.bins_x * A.d.bins_y;
     const int bx = bin % A.d.bins_x, by = bin / A.d.bins_x;
@@ -35,6 +41,7 @@ __global__ void __launch_bounds__(256) ncr_bin_coarse(NcrFlushArgs A) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ uint32_t s_count[8];
     __shared__ uint32_t s_base;
+    uint32_t* my_masks = ncr_coarse_masks + (size_t)warp * mask_words;
 
     const uint32_t n = A.n_cmds;
     const uint32_t seg = ((n + 7) / 8 + 31) & ~31u;   // per-warp segment, multiple of 32
@@ -49,8 +56,10 @@ __global__ void __launch_bounds__(256) ncr_bin_coarse(NcrFlushArgs A) {
             const NcrBox b = A.boxes[min(idx, n - 1)];   // unconditional (clamped) load: the four loads overlap
             hit[k] = box_hits(b, x0, y0, x1, y1) && idx < end;
         }
+        uint32_t m[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) count += __popc(__ballot_sync(0xffffffffu, hit[k]));
+        for (int k = 0; k < 4; ++k) { m[k] = __ballot_sync(0xffffffffu, hit[k]); count += __popc(m[k]); }
+        if (use_masks && lane < 4) my_masks[(base - beg) / 32 + lane] = lane == 0 ? m[0] : lane == 1 ? m[1] : lane == 2 ? m[2] : m[3];
     }
     if (lane == 0) s_count[warp] = count;
     __syncthreads();
@@ -68,6 +77,15 @@ __global__ void __launch_bounds__(256) ncr_bin_coarse(NcrFlushArgs A) {
     if (s_base == 0xffffffffu) return;
     uint32_t pos = s_base;
     for (int w = 0; w < warp; ++w) pos += s_count[w];
+    if (use_masks) {
+        if (count == 0) return;
+        for (uint32_t base = beg; base < end; base += 32) {   // replay: one mask word per 32 commands
+            const uint32_t m = my_masks[(base - beg) / 32];
+            if (m >> lane & 1u) A.coarse_list[pos + __popc(m & ((1u << lane) - 1))] = base + lane;
+            pos += __popc(m);
+        }
+        return;
+    }
     for (uint32_t base = beg; base < end; base += 128) {
         bool hit[4];
 #pragma unroll
@@ -259,7 +277,12 @@ extern "C" void ncr_launch_flush(const NcrFlushArgs* A, cudaStream_t s, cudaEven
     cudaMemsetAsync(A->cursors, 0, 8 * sizeof(uint32_t), s);
     if (ev) cudaEventRecord(ev[0], s);
     if (A->n_cmds) {
-        ncr_bin_coarse<<<n_bins, 256, 0, s>>>(*A);
+        // hit masks of the counting scan: one bit per command per CTA, rounded up to whole 128-command steps per warp
+        const uint32_t seg = ((A->n_cmds + 7) / 8 + 31) & ~31u;
+        const uint32_t mask_words = (seg + 127) / 128 * 4;
+        const size_t mask_bytes = (size_t)mask_words * 8 * sizeof(uint32_t);
+        const int use_masks = mask_bytes <= 40 * 1024;   // up to ~320 k commands per flush; beyond that the boxes are re-read
+        ncr_bin_coarse<<<n_bins, 256, use_masks ? mask_bytes : 0, s>>>(*A, use_masks, mask_words);
     } else {
         cudaMemsetAsync(A->coarse_off, 0, 2 * n_bins * sizeof(uint32_t), s);
     }
