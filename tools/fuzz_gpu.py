@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""Development helper: long fuzz campaign of the CUDA path against the CPU checkers (run under gpurun).
+
+    python tools/fuzz_gpu.py FIRST_SEED COUNT [--ref]   -> gpurun_out/fuzz.log
+
+Per seed: the randomised reference-ABI stream of tests/cases.py (five canvas shapes, three flushes each, u8 + f64 digests,
+YUV planes) against the C restatement, every 10th seed also against the unmodified reference build (--ref), plus the
+extension stream (clip / bilinear / polygon / perspective; parity unpinned) against the restatement."""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+import cases  # noqa: E402
+from libnativecpurenderer_b200 import streams  # noqa: E402
+from libnativecpurenderer_b200.binding import Renderer  # noqa: E402
+
+
+def main():
+    first, count = int(sys.argv[1]), int(sys.argv[2])
+    use_ref = "--ref" in sys.argv
+    gpu = Renderer()
+    port = Renderer(os.path.join(ROOT, "oracle", "libncr_oracle.so"))
+    ref = Renderer(os.path.join(ROOT, "oracle", "_ref", "libNativeCPURenderer.so")) if use_ref else None
+    img = np.load(os.path.join(ROOT, "tests", "golden", "image_rgba.npz"))["rgba"]
+    bad, t0 = [], time.time()
+    for seed in range(first, first + count):
+        run = cases.make_random_case(seed, use_apply_pixel=(seed % 2 == 0))
+        g = run(gpu, img)
+        if g != run(port, img):
+            bad.append(("abi/port", seed))
+        if ref is not None and seed % 10 == 1:   # odd seeds only: the reference build does not export ApplyPixel
+            if g != run(ref, img):
+                bad.append(("abi/ref", seed))
+        w, h, alpha = [(160, 90, True), (97, 61, False), (256, 144, True)][seed % 3]
+        got = []
+        for R in (gpu, port):
+            ctx = R.RenderContext(w, h, alpha)
+            tex = cases.tiny_textures(R, img)
+            tex.append(R.Texture(7, 6, True, np.random.RandomState(5).rand(6, 7, 4).tobytes(), is_uint8=False))
+            tex.append(R.Texture.from_numpy(np.random.RandomState(8).randint(0, 256, (12, 10, 3)).astype(np.uint8)))
+            streams.stream_extensions(ctx, tex, seed, n=80)
+            got.append((ctx.get_buffer_as_yuv420p().tobytes(), cases.digest(ctx)))
+        if got[0] != got[1]:
+            bad.append(("ext/port", seed))
+        if (seed - first) % 100 == 99:
+            print(f"{seed - first + 1} seeds, {len(bad)} mismatches, {time.time() - t0:.0f} s", flush=True)
+    print(f"DONE seeds {first}..{first + count - 1}: {len(bad)} mismatches {bad[:20]}")
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())
