@@ -60,7 +60,7 @@ struct NcrFramePool {
     long width = 0, height = 0;
     int alpha = 0;
     std::vector<RenderContext*> ctx;
-    std::vector<unsigned char*> buf;   // pinned, large enough for either present mode
+    std::vector<unsigned char*> buf;   // pinned, two per worker (render into one while the other waits for its turn at the sink)
     long u8_bytes = 0, yuv_bytes = 0;
 };
 
@@ -78,10 +78,13 @@ NcrFramePool* NcrCreateFramePool(long width, long height, int alpha, int n_worke
         if (!c) break;
         p->u8_bytes = GetBufferSize(c);
         p->yuv_bytes = NcrYUV420PSize(c);
-        unsigned char* b = (unsigned char*)NcrAllocHost((unsigned long long)std::max(p->u8_bytes, p->yuv_bytes));
-        if (!b) { DestroyRenderContext(c); break; }
+        const unsigned long long fb = (unsigned long long)std::max(p->u8_bytes, p->yuv_bytes);
+        unsigned char* b0 = (unsigned char*)NcrAllocHost(fb);
+        unsigned char* b1 = b0 ? (unsigned char*)NcrAllocHost(fb) : nullptr;
+        if (!b1) { if (b0) NcrFreeHost(b0); DestroyRenderContext(c); break; }
         p->ctx.push_back(c);
-        p->buf.push_back(b);
+        p->buf.push_back(b0);
+        p->buf.push_back(b1);
     }
     if (p->ctx.empty()) { delete p; return nullptr; }
     return p;
@@ -89,10 +92,8 @@ NcrFramePool* NcrCreateFramePool(long width, long height, int alpha, int n_worke
 
 void NcrDestroyFramePool(NcrFramePool* p) {
     if (!p) return;
-    for (size_t k = 0; k < p->ctx.size(); ++k) {
-        NcrFreeHost(p->buf[k]);
-        DestroyRenderContext(p->ctx[k]);
-    }
+    for (unsigned char* b : p->buf) NcrFreeHost(b);
+    for (RenderContext* c : p->ctx) DestroyRenderContext(c);
     delete p;
 }
 
@@ -107,9 +108,14 @@ long NcrFramePoolRender(NcrFramePool* p, const void* const* traces, const long* 
     const int n_workers = (int)std::min<long>((long)p->ctx.size(), n_frames);
     const long bytes = present == 1 ? p->yuv_bytes : p->u8_bytes;
 
+    // Frame f is rendered by worker f % n_workers into that worker's buffer (f / n_workers) % 2 and handed to a delivery
+    // thread, which calls the sink strictly in frame order; the worker goes on with its next frame in its other buffer and
+    // only waits when that buffer's previous frame (f - 2 n_workers) has not been delivered yet.  So one slow frame does
+    // not stall the pool, and the sink never runs concurrently with itself.
     std::mutex m;
     std::condition_variable cv;
-    long next = 0;
+    long delivered = 0;                       // frames [0, delivered) have been through the sink
+    std::vector<char> ready((size_t)n_frames, 0);
     bool failed = false;
     auto fail = [&]() {
         std::lock_guard<std::mutex> g(m);
@@ -119,10 +125,11 @@ long NcrFramePoolRender(NcrFramePool* p, const void* const* traces, const long* 
 
     auto worker = [&](int k) {
         RenderContext* ctx = p->ctx[k];
-        unsigned char* buf = p->buf[k];
-        for (long f = k; f < n_frames; f += n_workers) {
+        for (long f = k, j = 0; f < n_frames; f += n_workers, ++j) {
+            unsigned char* buf = p->buf[2 * k + (j & 1)];
             {
-                std::lock_guard<std::mutex> g(m);
+                std::unique_lock<std::mutex> g(m);
+                cv.wait(g, [&] { return failed || delivered > f - 2L * n_workers; });   // this buffer's previous frame is out
                 if (failed) break;
             }
             reset_state(ctx);
@@ -133,18 +140,30 @@ long NcrFramePoolRender(NcrFramePool* p, const void* const* traces, const long* 
             }
             if (ok && NcrFlush(ctx) != 0) ok = false;   // nothing pending: reports the context's sticky device-error state
             if (!ok) { fail(); break; }
-            std::unique_lock<std::mutex> g(m);
-            cv.wait(g, [&] { return next == f || failed; });
-            if (failed) break;
-            if (sink) sink(user, f, buf, bytes);   // in frame order, one at a time
-            next = f + 1;
+            std::lock_guard<std::mutex> g(m);
+            ready[(size_t)f] = 1;
+            cv.notify_all();
+        }
+    };
+    auto deliver = [&]() {
+        for (long f = 0; f < n_frames; ++f) {
+            {
+                std::unique_lock<std::mutex> g(m);
+                cv.wait(g, [&] { return failed || ready[(size_t)f]; });
+                if (failed) return;
+            }
+            if (sink) sink(user, f, p->buf[2 * (f % n_workers) + ((f / n_workers) & 1)], bytes);
+            std::lock_guard<std::mutex> g(m);
+            delivered = f + 1;
             cv.notify_all();
         }
     };
 
     std::vector<std::thread> pool;
     for (int k = 0; k < n_workers; ++k) pool.emplace_back(worker, k);
+    std::thread out(deliver);
     for (auto& t : pool) t.join();
+    out.join();
     return failed ? -1 : n_frames;
 }
 
