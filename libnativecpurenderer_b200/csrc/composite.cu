@@ -6,10 +6,11 @@
 // u8 -> k/255.0 decode table, so there are no block barriers in the command loop; warps pull half-tiles from
 // a global counter (persistent CTAs, one launch per flush).
 //
-// Per command the warp reads the parameters once through the read-only path at a warp-uniform address (one
-// L1 wavefront each) and amortises them over its 128 pixels; 8x4 blocks whose pixels all fall outside the
-// command's pixel box are skipped with one vote.  Texel fetches of the four pixels are issued back to back
-// before any is consumed.
+// Per command the warp stages the 240-byte command in a per-warp shared slot (the next one is fetched while the
+// current one is applied), reads its parameters as warp-uniform LDS broadcasts and amortises them over its 128
+// pixels; commands that provably miss the half-tile are rejected exactly during the list walk.  Texel fetches of
+// the four pixels are issued back to back before any is consumed.  The write-back produces, in the same pass, the
+// f64 canvas and — when asked — the (iu8)(v*255) image or its YUV 4:2:0 planes (present path).
 //
 // Arithmetic: the reference's f64 expression trees (reference src/libNativeCPURenderer.cpp, cited inline),
 // round-to-nearest intrinsics only, no FMA contraction.  Sub-expressions that do not depend on the pixel
@@ -241,9 +242,6 @@ __device__ __forceinline__ void shade_rgba8(const NcrCmd& c, uint32_t lut_base, 
     bool opaque[NCR_P];
     FOR4 {
         opaque[p] = false;
-#ifdef NCR_SLOT_SKIP
-        if (!__any_sync(FULL, in[p])) continue;   // no lane of this 8x4 block is covered
-#endif
         const uint32_t t = tx[p];
         double r = lut_byte<0>(lut_base, t), g = lut_byte<1>(lut_base, t), b = lut_byte<2>(lut_base, t);
         double a = lut_byte<3>(lut_base, t);
@@ -539,11 +537,7 @@ __device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A
 }
 
 template <bool ALPHA, bool COUNT>
-#ifdef NCR_MAXNREG
-__global__ void __maxnreg__(NCR_MAXNREG) ncr_composite(NcrFlushArgs A) {
-#else
 __global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, NCR_COMPOSITE_MIN_CTAS) ncr_composite(NcrFlushArgs A) {
-#endif
     // u8 / 255.0 (CreateTextureUInt8, cpp:350), IEEE division on both sides.  32 copies, copy c of entry k at [k*32 + c]:
     // a lane only ever reads its own copy, so lookups never collide on a bank.
     double* s_lut = (double*)ncr_smem;
