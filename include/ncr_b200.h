@@ -149,6 +149,12 @@ void NcrDrawTexturePerspective(RenderContext* ctx, Texture* tex, const double in
  * swing, 2x2-mean chroma) on the device, and read back only the planes: Y[h][w], U[ch][cw], V[ch][cw] with
  * cw = (w+1)/2, ch = (h+1)/2, contiguous in `out`.  Returns the bytes written (NcrYUV420PSize), -1 on failure.
  * libswscale's exact rounding cannot be checked here (FFmpeg absent): parity unpinned. */
+/* n sprites in one call: for k in 0..n-1 { SaveContextState; ApplyTransform(m6[k]) if m6; ApplyColorTransform(ct4[k]) if ct4;
+ * DrawSplittedTexture(tex, xywh[k], uv4[k]) if uv4 else DrawTexture(tex, xywh[k]); RestoreContextState } — exactly that call
+ * sequence (h:92-93,101,111,115,147), so bit-identical to the loop; m6 is [n][6] (a b c d e f), ct4 [n][4], xywh [n][4],
+ * uv4 [n][4] = uStart uEnd vStart vEnd.  Returns n, -1 on bad handles. */
+long NcrDrawTextureBatch(RenderContext* ctx, Texture* tex, long n, const double* m6, const double* ct4, const double* xywh,
+                         const double* uv4);
 /* Frame-parallel batch render (finishes reference pyb:302-367 MultiThreadedVideoRenderContextPreparer):
  * n_frames recorded frames (trace format as NcrSubmitTrace) are rendered by n_workers threads with one context / CUDA
  * stream each and delivered to `sink` strictly in frame order (pixels: the RGB(A)8 image for present 0, the YUV 4:2:0

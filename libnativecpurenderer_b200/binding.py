@@ -95,6 +95,7 @@ _EXT_ABI = {
     "NcrDrawTexturePerspective": (None, (_P, _P, _P) + (_D,) * 4),
     "NcrKernelLaunchCount": (c_ulonglong, ()),
     "NcrMeasureF64Rate": (c_double, ()),
+    "NcrDrawTextureBatch": (c_long, (_P, _P, c_long, _P, _P, _P, _P)),
     "NcrYUV420PSize": (c_long, (_P,)),
     "NcrGetBufferAsYUV420P": (c_long, (_P, _P)),
 }
@@ -379,6 +380,25 @@ class RenderContext:
 
     def get_buffer_as_yuv420p_into(self, address: int) -> int:
         return self._lib.NcrGetBufferAsYUV420P(self._ptr, c_void_p(address))
+
+    def draw_texture_batch(self, tex: "Texture", xywh, transforms=None, color_transforms=None, uv=None) -> int:
+        """n sprites in one FFI crossing (NcrDrawTextureBatch): per sprite save_state, apply_transform(transforms[k]),
+        apply_color_transform(color_transforms[k]), draw_texture / draw_splitted_texture(uv[k]), restore_state."""
+        import numpy as np
+
+        def arr(a, cols):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1, cols)
+            if a.shape[0] != n:
+                raise ValueError("array lengths differ")
+            return a
+
+        xywh = np.ascontiguousarray(xywh, dtype=np.float64).reshape(-1, 4)
+        n = xywh.shape[0]
+        m, ct, uvs = arr(transforms, 6), arr(color_transforms, 4), arr(uv, 4)
+        ptr = lambda a: None if a is None else c_void_p(a.ctypes.data)  # noqa: E731
+        return self._lib.NcrDrawTextureBatch(self._ptr, tex._ptr, n, ptr(m), ptr(ct), ptr(xywh), ptr(uvs))
 
     def draw_texture_perspective(self, tex: "Texture", inv_h, x, y, w, h):
         arr = (c_double * 9)(*[float(v) for v in inv_h])

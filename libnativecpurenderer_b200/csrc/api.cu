@@ -1367,6 +1367,25 @@ void NcrDrawTexturePerspective(RenderContext* ctx, Texture* tex_, const double i
     cmd->sx = tw / width; cmd->sy = th / height;
 }
 
+// Array form of the sprite idiom every reference host loops over (mil:977-1007, pyb:675-716):
+//     save_state; apply_transform(m[k]); apply_color_transform(ct[k]); draw_[splitted_]texture(tex, xywh[k][, uv[k]]); restore_state
+// for k = 0..n-1, in order, with ONE FFI crossing (a Python call costs ~2 us; a chart frame has ~16,000 of them).  It calls the
+// entry points above, so the result is the one the loop gives, bit for bit.
+long NcrDrawTextureBatch(RenderContext* ctx, Texture* tex, long n, const double* m6, const double* ct4, const double* xywh,
+                         const double* uv4) {
+    if (!live(ctx) || !live(tex) || n < 0 || (n > 0 && !xywh)) return -1;
+    for (long k = 0; k < n; ++k) {
+        SaveContextState(ctx);
+        if (m6) ApplyTransform(ctx, m6[6 * k], m6[6 * k + 1], m6[6 * k + 2], m6[6 * k + 3], m6[6 * k + 4], m6[6 * k + 5]);
+        if (ct4) ApplyColorTransform(ctx, ct4[4 * k], ct4[4 * k + 1], ct4[4 * k + 2], ct4[4 * k + 3]);
+        const double* r = xywh + 4 * k;
+        if (uv4) DrawSplittedTexture(ctx, tex, r[0], r[1], r[2], r[3], uv4[4 * k], uv4[4 * k + 1], uv4[4 * k + 2], uv4[4 * k + 3]);
+        else DrawTexture(ctx, tex, r[0], r[1], r[2], r[3]);
+        RestoreContextState(ctx);
+    }
+    return n;
+}
+
 long NcrSubmitTrace(RenderContext* ctx, const void* trace, long bytes, Texture* const* textures, long n_textures) {
     NcrContext* c = live(ctx);
     if (!c || !trace || bytes < 0) return -1;

@@ -554,3 +554,42 @@ def test_100k_tiny_draws_one_flush(gpu, port):
                 ctx.draw_circle(x, y, rng.uniform(.5, 4), rng.random(), rng.random(), rng.random(), rng.uniform(.1, 1))
         got.append(cases.digest(ctx))
     assert got[0] == got[1]
+
+
+def test_draw_texture_batch_equals_the_call_loop(gpu, port, image_rgba):
+    """NcrDrawTextureBatch: n sprites in one FFI crossing == the save / apply_transform / apply_color_transform / draw /
+    restore loop, bit for bit — against the product's own loop and against the C restatement's loop."""
+    import math
+    import random
+
+    rng = random.Random(5)
+    n = 400
+    m, ct, xywh, uv = [], [], [], []
+    for _ in range(n):
+        a, s = rng.uniform(0, 6.28), rng.uniform(.2, 1.5)
+        m.append([s * math.cos(a), s * math.sin(a), -s * math.sin(a), s * math.cos(a), rng.uniform(0, 480), rng.uniform(0, 270)])
+        ct.append([1, rng.uniform(.5, 1), rng.uniform(.5, 1), 1.0 if rng.random() < .2 else rng.uniform(.1, 1)])
+        xywh.append([-40, -30, 80, 60])
+        u0, v0 = rng.uniform(0, .5), rng.uniform(0, .5)
+        uv.append([u0, u0 + rng.uniform(.2, .5), v0, v0 + rng.uniform(.2, .5)])
+    out = {}
+    for name, R in (("gpu_batch", gpu), ("gpu_loop", gpu), ("port_loop", port)):
+        ctx = R.RenderContext(480, 270, True)
+        tex = R.Texture.from_numpy(image_rgba)
+        ctx.set_color(.1, .2, .3, 1)
+        ctx.translate(3, 4)          # an outer transform the batch composes with
+        for split in (False, True):
+            if name == "gpu_batch":
+                assert ctx.draw_texture_batch(tex, xywh, m, ct, uv if split else None) == n
+            else:
+                for k in range(n):
+                    ctx.save_state()
+                    ctx.apply_transform(*m[k])
+                    ctx.apply_color_transform(*ct[k])
+                    if split:
+                        ctx.draw_splitted_texture(tex, *xywh[k], *uv[k])
+                    else:
+                        ctx.draw_texture(tex, *xywh[k])
+                    ctx.restore_state()
+        out[name] = cases.digest(ctx)
+    assert out["gpu_batch"] == out["gpu_loop"] == out["port_loop"]
