@@ -593,3 +593,53 @@ def test_draw_texture_batch_equals_the_call_loop(gpu, port, image_rgba):
                     ctx.restore_state()
         out[name] = cases.digest(ctx)
     assert out["gpu_batch"] == out["gpu_loop"] == out["port_loop"]
+
+
+def test_first_use_from_many_threads_at_once():
+    """Device selection happens on first use; a fresh process whose first library calls come from 8 threads at the same
+    time (what a frame pool or a threaded host does) must initialise once and give every thread a working context."""
+    import subprocess
+    import sys
+
+    code = r"""
+import sys, threading
+sys.path.insert(0, %r)
+from libnativecpurenderer_b200.binding import Renderer
+R = Renderer()
+out, go = [None] * 8, threading.Barrier(8)
+def work(k):
+    go.wait()
+    ctx = R.RenderContext(64, 32, True)
+    ctx.set_color(k / 8.0, 0, 0, 1)
+    out[k] = bytes(ctx.get_buffer_as_uint8())[:4]
+ts = [threading.Thread(target=work, args=(k,)) for k in range(8)]
+[t.start() for t in ts]; [t.join() for t in ts]
+assert out == [bytes([int(k / 8.0 * 255), 0, 0, 255]) for k in range(8)], out
+print("ok")
+""" % (str(__import__("pathlib").Path(__file__).resolve().parents[1]),)
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and res.stdout.strip().endswith("ok"), res.stdout + res.stderr
+
+
+def test_frame_pool_reports_bad_frames(gpu, image_rgba):
+    """A malformed trace in the middle of a batch fails the whole render (-1 -> RuntimeError) without hanging the pool, and
+    the pool is usable afterwards."""
+    from libnativecpurenderer_b200 import batch
+
+    tex = [gpu.Texture.from_numpy(image_rgba)]
+    def frame(k):
+        rec = trace.TraceRecorder(96, 64, True)
+        rec.set_color(0, 0, k / 10.0, 1)
+        rec.draw_texture(trace.TexSlot(0, 128, 128), 5 + k, 5, 40, 40)
+        rec.present()
+        return rec.as_array()
+    good = [frame(k) for k in range(9)]
+    bad = list(good)
+    broken = good[4].copy()
+    broken.view(np.uint32)[11] = 0x7fffffff         # argument count of the 2nd record (DrawTexture): runs past the end of the trace
+    bad[4] = broken
+    with batch.FramePool(gpu, 96, 64, True, workers=3) as pool:
+        with pytest.raises((RuntimeError, ValueError)):
+            pool.render(bad, tex)
+        seen = []
+        assert pool.render(good, tex, on_frame=lambda i, px: seen.append(i)) == 9 and seen == list(range(9))
