@@ -45,7 +45,8 @@ def build_variant(name: str, defines: list[str]) -> str:
     objs = []
     for src in SOURCES:
         obj = os.path.join(out_dir, src.rsplit(".", 1)[0] + ".o")
-        cmd = [NVCC, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
+        extra = os.environ.get("NCR_EXTRA_NVCC", "").split()   # development: extra compiler flags for an A/B build
+        cmd = [NVCC, *NVCC_FLAGS, *extra, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             sys.stderr.write(res.stdout + res.stderr)
