@@ -302,7 +302,7 @@ def run_product(args) -> None:
     ctx.get_buffer_as_uint8_into(pinned)
     n_cmds, fine_entries, blended = st.n_cmds, st.fine_entries, st.blended_pixels
     aux_bytes = 0
-    h2d = n_cmds * (240 + 16) + aux_bytes
+    h2d = n_cmds * (240 + 16 + 4) + aux_bytes
 
     # ---- value: K steps from resident buffers -------------------------------------------------------------
     K, W = args.steps, max(args.warmup, 3)

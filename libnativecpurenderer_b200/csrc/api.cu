@@ -181,6 +181,7 @@ struct NcrTexture {
 struct NcrStaging {
     PinnedVec<NcrCmd> cmds;
     PinnedVec<NcrBox> boxes;
+    PinnedVec<uint32_t> binbox;   // the box in 128-px bin coordinates, 4 x u8 (what ncr_bin_coarse reads)
     PinnedVec<double> aux;
     cudaEvent_t done = nullptr;
     bool inflight = false;
@@ -206,6 +207,7 @@ struct NcrContext {
     // device side
     DevVec<NcrCmd> d_cmds;
     DevVec<NcrBox> d_boxes;
+    DevVec<uint32_t> d_binbox;
     DevVec<double> d_aux;
     DevVec<uint32_t> d_coarse, d_coarse_off, d_fine, d_fine_off, d_cursors;
     DevVec<unsigned char> d_u8;
@@ -400,26 +402,29 @@ bool flush(NcrContext* c, bool want_u8, bool want_yuv = false) {
     frame_dims(c, &A.d);
     const size_t n_tiles = (size_t)A.d.tiles_x * A.d.tiles_y, n_bins = (size_t)A.d.bins_x * A.d.bins_y;
     NcrStaging& S = c->stg[c->cur];
-    bool ok = c->d_cmds.reserve(c->n) && c->d_boxes.reserve(c->n) && c->d_aux.reserve(c->n_aux + 2) &&
+    bool ok = c->d_cmds.reserve(c->n) && c->d_boxes.reserve(c->n) && c->d_binbox.reserve(c->n) && c->d_aux.reserve(c->n_aux + 2) &&
               c->d_coarse.reserve(c->coarse_need + 1) && c->d_coarse_off.reserve(2 * n_bins) &&
               c->d_fine.reserve(c->fine_need + 1) && c->d_fine_off.reserve(2 * n_tiles) && c->d_cursors.reserve(8);
     if (ok && want_u8) ok = c->d_u8.reserve(n_elems);
     if (ok && want_yuv) ok = c->d_yuv.reserve(yuv_bytes_of(c));
     if (!ok) { c->failed = true; return false; }
     ok = CK(cudaMemcpyAsync(c->d_cmds.p, S.cmds.p, c->n * sizeof(NcrCmd), cudaMemcpyHostToDevice, c->stream)) &&
-         CK(cudaMemcpyAsync(c->d_boxes.p, S.boxes.p, c->n * sizeof(NcrBox), cudaMemcpyHostToDevice, c->stream));
+         CK(cudaMemcpyAsync(c->d_boxes.p, S.boxes.p, c->n * sizeof(NcrBox), cudaMemcpyHostToDevice, c->stream)) &&
+         CK(cudaMemcpyAsync(c->d_binbox.p, S.binbox.p, c->n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     if (ok && c->n_aux)
         ok = CK(cudaMemcpyAsync(c->d_aux.p, S.aux.p, c->n_aux * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     if (!ok) { c->failed = true; return false; }
     cudaEventRecord(S.done, c->stream);
     S.inflight = true;
-    c->stats.h2d_bytes += c->n * (sizeof(NcrCmd) + sizeof(NcrBox)) + c->n_aux * sizeof(double);
+    c->stats.h2d_bytes += c->n * (sizeof(NcrCmd) + sizeof(NcrBox) + sizeof(uint32_t)) + c->n_aux * sizeof(double);
 
     A.fb = (double*)c->fb->p;
     A.u8_out = want_u8 ? c->d_u8.p : nullptr;
     A.yuv_out = want_yuv ? c->d_yuv.p : nullptr;
     A.cmds = c->d_cmds.p;
     A.boxes = c->d_boxes.p;
+    // bin coordinates fit in a byte up to 255 bins (32,640 px) per axis; larger canvases bin from the full boxes
+    A.binboxes = (c->w <= 255 * NCR_TILE * NCR_COARSE && c->h <= 255 * NCR_TILE * NCR_COARSE) ? c->d_binbox.p : nullptr;
     A.aux = c->d_aux.p;
     A.n_cmds = (uint32_t)c->n;
     A.load_fb = c->load_fb ? 1u : 0u;
@@ -464,7 +469,7 @@ bool reserve_cmd(NcrContext* c, size_t extra_aux) {
         S.inflight = false;
     }
     if (c->n + 1 > S.cmds.cap) {
-        if (!S.cmds.reserve(c->n + 1, c->n) || !S.boxes.reserve(S.cmds.cap, c->n)) return false;
+        if (!S.cmds.reserve(c->n + 1, c->n) || !S.boxes.reserve(S.cmds.cap, c->n) || !S.binbox.reserve(S.cmds.cap, c->n)) return false;
     }
     if (c->n_aux + extra_aux > S.aux.cap) {
         if (!S.aux.reserve(c->n_aux + extra_aux, c->n_aux)) return false;
@@ -511,6 +516,12 @@ NcrCmd* begin_cmd(NcrContext* c, uint32_t op, i64 l, i64 r, i64 t, i64 b, bool c
     bx.l = cmd->l; bx.r = cmd->r; bx.t = cmd->t; bx.b = cmd->b;
     const unsigned long long tx = ((r - 1) / NCR_TILE) - (l / NCR_TILE) + 1, ty = ((b - 1) / NCR_TILE) - (t / NCR_TILE) + 1;
     const i64 edge = NCR_TILE * NCR_COARSE;
+    if (l < r && t < b) {   // first / last bin touched, per axis (l < x1 <=> l/edge <= bin; r > x0 <=> (r-1)/edge >= bin)
+        S.binbox.p[c->n] = (uint32_t)std::min<i64>(l / edge, 255) | ((uint32_t)std::min<i64>((r - 1) / edge, 255) << 8) |
+                           ((uint32_t)std::min<i64>(t / edge, 255) << 16) | ((uint32_t)std::min<i64>((b - 1) / edge, 255) << 24);
+    } else {
+        S.binbox.p[c->n] = 0x00010001u;   // first > last on both axes: touches no bin
+    }
     const unsigned long long bxn = ((r - 1) / edge) - (l / edge) + 1, byn = ((b - 1) / edge) - (t / edge) + 1;
     c->fine_need += tx * ty;
     c->coarse_need += bxn * byn;
@@ -652,11 +663,11 @@ void DestroyRenderContext(RenderContext* ctx) {
     c->fb.reset();
     c->refs.clear();
     c->last_refs.clear();
-    c->d_cmds.release(); c->d_boxes.release(); c->d_aux.release();
+    c->d_cmds.release(); c->d_boxes.release(); c->d_binbox.release(); c->d_aux.release();
     c->d_coarse.release(); c->d_coarse_off.release(); c->d_fine.release(); c->d_fine_off.release();
     c->d_cursors.release(); c->d_u8.release(); c->d_yuv.release();
     for (int k = 0; k < 2; ++k) {
-        c->stg[k].cmds.release(); c->stg[k].boxes.release(); c->stg[k].aux.release();
+        c->stg[k].cmds.release(); c->stg[k].boxes.release(); c->stg[k].binbox.release(); c->stg[k].aux.release();
         if (c->stg[k].done) cudaEventDestroy(c->stg[k].done);
     }
     for (int k = 0; k < 4; ++k) cudaEventDestroy(c->ev[k]);

@@ -31,6 +31,7 @@ __device__ __forceinline__ bool box_hits(const NcrBox& bx, int x0, int y0, int x
 // is L2-bandwidth bound (bins x commands x 16 B per pass), so this halves its traffic.  The host enables it whenever the
 // masks fit (n_cmds / 8 bits per CTA).
 extern __shared__ uint32_t ncr_coarse_masks[];
+#define NCR_COARSE_U 8
 
 __global__ void __launch_bounds__(256) ncr_bin_coarse(NcrFlushArgs A, int use_masks, uint32_t mask_words) {
     const int bin = blockIdx.x;
@@ -48,18 +49,35 @@ __global__ void __launch_bounds__(256) ncr_bin_coarse(NcrFlushArgs A, int use_ma
     const uint32_t beg = min(n, warp * seg), end = min(n, beg + seg);
 
     uint32_t count = 0;
-    for (uint32_t base = beg; base < end; base += 128) {
-        bool hit[4];
+    const uint32_t* __restrict__ bb = A.binboxes;
+    // The scan is bound by the round trip of its loads, not by their bytes: NCR_COARSE_U independent loads per lane are
+    // in flight per step (one command per lane per load, so a ballot is already in submission order).
+    for (uint32_t base = beg; base < end; base += 32 * NCR_COARSE_U) {
+        bool hit[NCR_COARSE_U];
+        if (bb) {   // 4 bytes per command: the box in bin coordinates (host-computed)
+            uint32_t q[NCR_COARSE_U];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t idx = base + k * 32 + lane;
-            const NcrBox b = A.boxes[min(idx, n - 1)];   // unconditional (clamped) load: the four loads overlap
-            hit[k] = box_hits(b, x0, y0, x1, y1) && idx < end;
+            for (int k = 0; k < NCR_COARSE_U; ++k) q[k] = bb[min(base + k * 32 + lane, n - 1)];   // clamped, unconditional
+#pragma unroll
+            for (int k = 0; k < NCR_COARSE_U; ++k)
+                hit[k] = (uint32_t)bx >= (q[k] & 255u) && (uint32_t)bx <= ((q[k] >> 8) & 255u) &&
+                         (uint32_t)by >= ((q[k] >> 16) & 255u) && (uint32_t)by <= (q[k] >> 24) && base + k * 32 + lane < end;
+        } else {
+#pragma unroll
+            for (int k = 0; k < NCR_COARSE_U; ++k) {
+                const uint32_t idx = base + k * 32 + lane;
+                const NcrBox b = A.boxes[min(idx, n - 1)];   // unconditional (clamped) load: the loads overlap
+                hit[k] = box_hits(b, x0, y0, x1, y1) && idx < end;
+            }
         }
-        uint32_t m[4];
+        uint32_t mine = 0;   // lane k keeps ballot k of this step
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { m[k] = __ballot_sync(0xffffffffu, hit[k]); count += __popc(m[k]); }
-        if (use_masks && lane < 4) my_masks[(base - beg) / 32 + lane] = lane == 0 ? m[0] : lane == 1 ? m[1] : lane == 2 ? m[2] : m[3];
+        for (int k = 0; k < NCR_COARSE_U; ++k) {
+            const uint32_t m = __ballot_sync(0xffffffffu, hit[k]);
+            count += __popc(m);
+            if (lane == k) mine = m;
+        }
+        if (use_masks && lane < NCR_COARSE_U) my_masks[(base - beg) / 32 + lane] = mine;
     }
     if (lane == 0) s_count[warp] = count;
     __syncthreads();
@@ -279,7 +297,7 @@ extern "C" void ncr_launch_flush(const NcrFlushArgs* A, cudaStream_t s, cudaEven
     if (A->n_cmds) {
         // hit masks of the counting scan: one bit per command per CTA, rounded up to whole 128-command steps per warp
         const uint32_t seg = ((A->n_cmds + 7) / 8 + 31) & ~31u;
-        const uint32_t mask_words = (seg + 127) / 128 * 4;
+        const uint32_t mask_words = (seg + 32 * NCR_COARSE_U - 1) / (32 * NCR_COARSE_U) * NCR_COARSE_U;
         const size_t mask_bytes = (size_t)mask_words * 8 * sizeof(uint32_t);
         const int use_masks = mask_bytes <= 40 * 1024;   // up to ~320 k commands per flush; beyond that the boxes are re-read
         ncr_bin_coarse<<<n_bins, 256, use_masks ? mask_bytes : 0, s>>>(*A, use_masks, mask_words);

@@ -79,6 +79,7 @@ struct NcrFlushArgs {
     unsigned char* yuv_out;     // fused YUV 4:2:0 planes of that image (present path), or nullptr
     const NcrCmd* cmds;
     const NcrBox* boxes;
+    const uint32_t* binboxes;   // per command: first/last 128-px bin touched per axis, 4 x u8 (x0 x1 y0 y1), or nullptr
     const double* aux;
     uint32_t n_cmds;
     uint32_t load_fb;           // 0: every tile's list starts with SET_COLOR, do not read fb
