@@ -32,6 +32,7 @@ __device__ __forceinline__ bool box_hits(const NcrBox& bx, int x0, int y0, int x
 // masks fit (n_cmds / 8 bits per CTA).
 extern __shared__ uint32_t ncr_coarse_masks[];
 #define NCR_COARSE_U 8
+#define NCR_FINE_U 4
 
 __global__ void __launch_bounds__(256) ncr_bin_coarse(NcrFlushArgs A, int use_masks, uint32_t mask_words) {
     const int bin = blockIdx.x;
@@ -170,18 +171,19 @@ __global__ void __launch_bounds__(256) ncr_bin_fine(NcrFlushArgs A) {
         }
         return;
     }
-    for (uint32_t k = 0; k < ccount; k += 128) {
-        uint32_t idx[4];
-        bool hit[4];
+    // longer lists: NCR_FINE_U independent index -> box chains per lane per step (the scan is round-trip bound)
+    for (uint32_t k = 0; k < ccount; k += 32 * NCR_FINE_U) {
+        uint32_t idx[NCR_FINE_U];
+        bool hit[NCR_FINE_U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) idx[u] = A.coarse_list[cbase + min(k + u * 32 + lane, ccount - 1)];   // clamped, unconditional
+        for (int u = 0; u < NCR_FINE_U; ++u) idx[u] = A.coarse_list[cbase + min(k + u * 32 + lane, ccount - 1)];   // clamped, unconditional
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < NCR_FINE_U; ++u) {
             const NcrBox b = A.boxes[idx[u]];
             hit[u] = box_hits(b, x0, y0, x1, y1) && (k + u * 32 + lane < ccount);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) count += __popc(__ballot_sync(0xffffffffu, hit[u]));
+        for (int u = 0; u < NCR_FINE_U; ++u) count += __popc(__ballot_sync(0xffffffffu, hit[u]));
     }
     uint32_t off = 0;
     if (lane == 0) {
@@ -193,18 +195,18 @@ __global__ void __launch_bounds__(256) ncr_bin_fine(NcrFlushArgs A) {
     off = __shfl_sync(0xffffffffu, off, 0);
     count = __shfl_sync(0xffffffffu, count, 0);
     if (count == 0) return;
-    for (uint32_t k = 0; k < ccount; k += 128) {
-        uint32_t idx[4];
-        bool hit[4];
+    for (uint32_t k = 0; k < ccount; k += 32 * NCR_FINE_U) {
+        uint32_t idx[NCR_FINE_U];
+        bool hit[NCR_FINE_U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) idx[u] = A.coarse_list[cbase + min(k + u * 32 + lane, ccount - 1)];   // clamped, unconditional
+        for (int u = 0; u < NCR_FINE_U; ++u) idx[u] = A.coarse_list[cbase + min(k + u * 32 + lane, ccount - 1)];   // clamped, unconditional
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < NCR_FINE_U; ++u) {
             const NcrBox b = A.boxes[idx[u]];
             hit[u] = box_hits(b, x0, y0, x1, y1) && (k + u * 32 + lane < ccount);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < NCR_FINE_U; ++u) {
             const uint32_t m = __ballot_sync(0xffffffffu, hit[u]);
             if (hit[u]) A.fine_list[off + __popc(m & ((1u << lane) - 1))] = idx[u];
             off += __popc(m);
