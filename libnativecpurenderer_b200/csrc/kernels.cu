@@ -22,7 +22,7 @@ __device__ __forceinline__ bool box_hits(const NcrBox& bx, int x0, int y0, int x
     return bx.l < bx.r && bx.t < bx.b && bx.l < x1 && bx.r > x0 && bx.t < y1 && bx.b > y0;
 }
 
-// One CTA per 128x128-px bin.  The command range is cut into 8 contiguous segments, one per warp; each warp counts its
+// One CTA per 128x128-px bin.  The command range is cut into NCR_COARSE_WARPS contiguous segments, one per warp; each warp counts its
 // hits (ballot + popc, four independent box loads in flight per lane), one block-level prefix gives every warp its write
 // position, and the warps re-scan their segments writing command indices in submission order.  No barrier inside the
 // loops.  Lists of different bins are carved out of one array with a single atomicAdd per bin.
@@ -34,19 +34,20 @@ extern __shared__ uint32_t ncr_coarse_masks[];
 #define NCR_COARSE_U 8
 #define NCR_FINE_U 4
 
-__global__ void __launch_bounds__(256) ncr_bin_coarse(NcrFlushArgs A, int use_masks, uint32_t mask_words) {
+#define NCR_COARSE_WARPS 8   // warps per bin: the command range is cut into this many contiguous segments
+__global__ void __launch_bounds__(32 * NCR_COARSE_WARPS) ncr_bin_coarse(NcrFlushArgs A, int use_masks, uint32_t mask_words) {
     const int bin = blockIdx.x;
     const int n_bins = A.d.bins_x * A.d.bins_y;
     const int bx = bin % A.d.bins_x, by = bin / A.d.bins_x;
     const int edge = NCR_TILE * NCR_COARSE;
     const int x0 = bx * edge, y0 = by * edge, x1 = x0 + edge, y1 = y0 + edge;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __shared__ uint32_t s_count[8];
+    __shared__ uint32_t s_count[NCR_COARSE_WARPS];
     __shared__ uint32_t s_base;
     uint32_t* my_masks = ncr_coarse_masks + (size_t)warp * mask_words;
 
     const uint32_t n = A.n_cmds;
-    const uint32_t seg = ((n + 7) / 8 + 31) & ~31u;   // per-warp segment, multiple of 32
+    const uint32_t seg = ((n + NCR_COARSE_WARPS - 1) / NCR_COARSE_WARPS + 31) & ~31u;   // per-warp segment, multiple of 32
     const uint32_t beg = min(n, warp * seg), end = min(n, beg + seg);
 
     uint32_t count = 0;
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(256) ncr_bin_coarse(NcrFlushArgs A, int use_ma
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t total = 0;
-        for (int w = 0; w < 8; ++w) total += s_count[w];
+        for (int w = 0; w < NCR_COARSE_WARPS; ++w) total += s_count[w];
         uint32_t off = atomicAdd(&A.cursors[0], total);
         if (off + total > A.coarse_cap) { total = 0; atomicExch(&A.cursors[4], 1u); }
         s_base = off;
@@ -298,11 +299,11 @@ extern "C" void ncr_launch_flush(const NcrFlushArgs* A, cudaStream_t s, cudaEven
     if (ev) cudaEventRecord(ev[0], s);
     if (A->n_cmds) {
         // hit masks of the counting scan: one bit per command per CTA, rounded up to whole 128-command steps per warp
-        const uint32_t seg = ((A->n_cmds + 7) / 8 + 31) & ~31u;
+        const uint32_t seg = ((A->n_cmds + NCR_COARSE_WARPS - 1) / NCR_COARSE_WARPS + 31) & ~31u;
         const uint32_t mask_words = (seg + 32 * NCR_COARSE_U - 1) / (32 * NCR_COARSE_U) * NCR_COARSE_U;
-        const size_t mask_bytes = (size_t)mask_words * 8 * sizeof(uint32_t);
+        const size_t mask_bytes = (size_t)mask_words * NCR_COARSE_WARPS * sizeof(uint32_t);
         const int use_masks = mask_bytes <= 40 * 1024;   // up to ~320 k commands per flush; beyond that the boxes are re-read
-        ncr_bin_coarse<<<n_bins, 256, use_masks ? mask_bytes : 0, s>>>(*A, use_masks, mask_words);
+        ncr_bin_coarse<<<n_bins, 32 * NCR_COARSE_WARPS, use_masks ? mask_bytes : 0, s>>>(*A, use_masks, mask_words);
     } else {
         cudaMemsetAsync(A->coarse_off, 0, 2 * n_bins * sizeof(uint32_t), s);
     }
