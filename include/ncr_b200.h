@@ -117,8 +117,16 @@ typedef struct NcrStats {
     unsigned long long flushes;         /* cumulative */
     unsigned long long kernel_launches; /* cumulative, this context */
     float ms_bin_coarse, ms_bin_fine, ms_composite, ms_total; /* last flush, CUDA events (stats mode & 2) */
+    unsigned long long materialized;    /* cumulative: batches re-run to bring a stale f64 canvas up to date (see NcrRerunLastFlushEx) */
 } NcrStats;
 
+/* Devices.  CreateRenderContext / CreateTexture* (section 1) use the process default device: NCR_DEVICE, else LOCAL_RANK,
+ * else 0 — what a one-process-per-GPU launcher wants.  A single host process (reference src/milrenderer.py is one,
+ * mil:865-1038; its own sketch allocates a block of contexts in-process, pyb:362-364) places contexts explicitly; a texture
+ * is copied to a device the first time a context on that device draws it, so textures are created once, as in the reference. */
+int NcrDeviceCount(void);                          /* usable CUDA devices, 0 without one */
+RenderContext* NcrCreateRenderContextOnDevice(long width, long height, bool enableAlpha, int device);
+int NcrContextDevice(RenderContext* ctx);          /* device a context lives on, -1 for a bad handle */
 int NcrFlush(RenderContext* ctx);                  /* submit pending draws and wait; 0 on success */
 const char* NcrLastError(void);                    /* last device/runtime error text ("" if none) */
 const char* NcrDeviceName(void);                   /* name of the CUDA device in use, "" before first use */
@@ -133,6 +141,13 @@ long NcrSubmitTrace(RenderContext* ctx, const void* trace, long bytes, Texture* 
  * stream: {whole step, ncr_bin_coarse, ncr_bin_fine, ncr_composite}; flush_l2 != 0 overwrites a buffer larger than
  * L2 before each iteration (outside the timed span). */
 int NcrRerunLastFlush(RenderContext* ctx, int iters, int flush_l2, float* ms_out);
+/* The same with the two launch modes of a flush made explicit (-1 = as the batch was flushed):
+ *   write_fb  1: the composite writes the f64 canvas back (what GetBuffer / a following draw needs);
+ *             0: present-only — GetBufferAsUInt8 / NcrGetBufferAsYUV420P flushes skip the canvas write-back (the canvas is
+ *                marked stale and the resident batch is re-run with write_fb = 1 if anything ever reads it; a video frame's
+ *                canvas never is, its successor starts with SetColor);
+ *   prefetch  1/0: composite variant with / without cross-region prefetch of the next region's list and first command. */
+int NcrRerunLastFlushEx(RenderContext* ctx, int iters, int flush_l2, float* ms_out, int write_fb, int prefetch);
 void NcrGetStats(RenderContext* ctx, NcrStats* out);
 void NcrSetStatsMode(RenderContext* ctx, int mode); /* bit 0: count blended pixels, bit 1: per-kernel events */
 unsigned long long NcrKernelLaunchCount(void);      /* kernels launched by this library since load (all contexts) */
@@ -166,6 +181,9 @@ long NcrRenderFrames(long width, long height, int alpha, const void* const* trac
 /* The same with the worker contexts, their device buffers and pinned frame buffers kept between calls. */
 typedef struct NcrFramePool NcrFramePool;
 NcrFramePool* NcrCreateFramePool(long width, long height, int alpha, int n_workers);   /* NULL without a usable device */
+/* The same pool spread over several devices of the box: worker k renders on devices[k % n_devices]; frames are still
+ * delivered in order to one sink.  One host process drives all the GPUs (no torchrun, no collective). */
+NcrFramePool* NcrCreateFramePoolOnDevices(long width, long height, int alpha, int n_workers, const int* devices, int n_devices);
 void NcrDestroyFramePool(NcrFramePool* pool);
 int NcrFramePoolWorkers(NcrFramePool* pool);
 long NcrFramePoolRender(NcrFramePool* pool, const void* const* traces, const long* trace_bytes, long n_frames,

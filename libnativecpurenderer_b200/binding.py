@@ -85,7 +85,12 @@ _EXT_ABI = {
     "NcrAllocHost": (_P, (c_ulonglong,)),
     "NcrFreeHost": (None, (_P,)),
     "NcrSubmitTrace": (c_long, (_P, _P, c_long, _P, c_long)),
+    "NcrDeviceCount": (c_int, ()),
+    "NcrCreateRenderContextOnDevice": (_P, (c_long, c_long, c_bool, c_int)),
+    "NcrContextDevice": (c_int, (_P,)),
+    "NcrCreateFramePoolOnDevices": (_P, (c_long, c_long, c_int, c_int, _P, c_int)),
     "NcrRerunLastFlush": (c_int, (_P, c_int, c_int, _P)),
+    "NcrRerunLastFlushEx": (c_int, (_P, c_int, c_int, _P, c_int, c_int)),
     "NcrGetStats": (None, (_P, _P)),
     "NcrSetStatsMode": (None, (_P, c_int)),
     "NcrSetClipRect": (None, (_P, c_long, c_long, c_long, c_long)),
@@ -117,6 +122,7 @@ class NcrStats(ctypes.Structure):
         ("ms_bin_fine", c_float),
         ("ms_composite", c_float),
         ("ms_total", c_float),
+        ("materialized", c_ulonglong),
     ]
 
 

@@ -36,12 +36,15 @@
 namespace {
 
 std::mutex g_mu;
-int g_dev = -1;
+int g_dev = -1;   // default device of this process: NCR_DEVICE, else LOCAL_RANK, else 0
 int g_init = 0;   // 0 untried, 1 ok, -1 failed
 char g_err[512] = "";
-char g_devname[256] = "";
+const int kMaxDevices = 64;
+int g_n_devices = 0;
+char g_devname[kMaxDevices][256];
+std::atomic<int> g_dev_ok[kMaxDevices];   // 0 unchecked, 1 usable (sm_100), -1 not
 std::atomic<unsigned long long> g_launches{0};
-void* g_l2_scrub = nullptr;
+void* g_l2_scrub[kMaxDevices];
 const size_t kL2ScrubBytes = 256u << 20;
 
 void set_error(const char* what, const char* detail) {
@@ -57,16 +60,19 @@ bool ck(cudaError_t e, const char* what) {
 }
 #define CK(call) ck((call), #call)
 
-// Selects the device once (NCR_DEVICE, else LOCAL_RANK, else 0) and makes it current on the calling thread.
+// Device bookkeeping.  A context (canvas, stream, recorder, device buffers) lives on ONE device, chosen at creation: the
+// process default (NCR_DEVICE, else LOCAL_RANK, else 0 — what one-process-per-GPU launchers such as torchrun want) or an
+// explicit one (NcrCreateRenderContextOnDevice / NcrCreateFramePoolOnDevices — what a single host process such as
+// milrenderer.py needs to use a multi-GPU box).  Every entry point that touches CUDA makes its context's device current on
+// the calling thread first; textures are replicated to a device the first time a context on it draws them.
 std::mutex g_init_mu;
 std::atomic<int> g_init_done{0};   // published copy of g_init for the lock-free fast path
 
-bool use_device() {
-    if (g_init_done.load(std::memory_order_acquire) == 1) return cudaSetDevice(g_dev) == cudaSuccess;
+bool init_runtime() {
+    if (g_init_done.load(std::memory_order_acquire) != 0) return g_init_done.load(std::memory_order_acquire) == 1;
     std::lock_guard<std::mutex> init_lock(g_init_mu);   // first use from several threads at once (frame pool, tests)
     struct Publish { ~Publish() { g_init_done.store(g_init, std::memory_order_release); } } publish;
-    if (g_init == 1) return cudaSetDevice(g_dev) == cudaSuccess;
-    if (g_init == -1) return false;
+    if (g_init != 0) return g_init == 1;
     int want = 0;
     const char* env = getenv("NCR_DEVICE");
     if (!env || !*env) env = getenv("LOCAL_RANK");
@@ -79,25 +85,43 @@ bool use_device() {
         g_init = -1;
         return false;
     }
-    if (want < 0 || want >= count) want = want % count;
-    if (!CK(cudaSetDevice(want))) { g_init = -1; return false; }
-    cudaDeviceProp prop;
-    if (!CK(cudaGetDeviceProperties(&prop, want))) { g_init = -1; return false; }
-    if (prop.major < 10) {
-        char msg[160];
-        snprintf(msg, sizeof(msg), "%s is sm_%d%d; the kernels are built for sm_100a only", prop.name, prop.major, prop.minor);
-        set_error("unsupported device", msg);
-        g_init = -1;
-        return false;
-    }
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        snprintf(g_devname, sizeof(g_devname), "%s", prop.name);
-    }
+    g_n_devices = std::min(count, kMaxDevices);
+    if (want < 0 || want >= g_n_devices) want = ((want % g_n_devices) + g_n_devices) % g_n_devices;
     g_dev = want;
     g_init = 1;
     return true;
 }
+
+// Makes `dev` current on the calling thread (checking once that it is an sm_100 part).
+bool set_device(int dev) {
+    if (!init_runtime()) return false;
+    if (dev < 0 || dev >= g_n_devices) { set_error("device index", "out of range"); return false; }
+    int ok = g_dev_ok[dev].load(std::memory_order_acquire);
+    if (ok == 0) {
+        std::lock_guard<std::mutex> init_lock(g_init_mu);
+        ok = g_dev_ok[dev].load(std::memory_order_acquire);
+        if (ok == 0) {
+            cudaDeviceProp prop;
+            ok = -1;
+            if (CK(cudaSetDevice(dev)) && CK(cudaGetDeviceProperties(&prop, dev))) {
+                if (prop.major < 10) {
+                    char msg[400];
+                    snprintf(msg, sizeof(msg), "%.200s is sm_%d%d; the kernels are built for sm_100a only", prop.name, prop.major, prop.minor);
+                    set_error("unsupported device", msg);
+                } else {
+                    std::lock_guard<std::mutex> lk(g_mu);
+                    snprintf(g_devname[dev], sizeof(g_devname[dev]), "%s", prop.name);
+                    ok = 1;
+                }
+            }
+            g_dev_ok[dev].store(ok, std::memory_order_release);
+        }
+    }
+    if (ok != 1) return false;
+    return cudaSetDevice(dev) == cudaSuccess;
+}
+
+bool use_device() { return init_runtime() && set_device(g_dev); }
 
 struct DevMem {
     void* p = nullptr;
@@ -173,9 +197,18 @@ struct NcrTexture {
     i64 w = 0, h = 0;
     bool alpha = false;
     bool is_f64 = false;
+    int dev = 0;                    // device that holds `buf`
     DevRef buf;                     // texels; null for an alias
     NcrContext* alias = nullptr;    // CreateTextureFromRenderContextShared: the canvas itself (cpp:382)
+    std::mutex mu;                  // guards replicas, shadow and the alias snapshot (textures are shared between contexts / threads)
+    std::vector<DevRef> replicas;   // [device]: copies of `buf` on other devices, made on first use there (slots never move)
+    std::atomic<unsigned long long> replica_mask{0};   // bit d: replicas[d] is published
     std::vector<unsigned char> shadow;   // host copy of u8 texels, fetched on demand (hit-effect masks)
+    // alias only: snapshot of the source canvas, reused while the source records nothing new (NcrContext::gen)
+    DevRef snap;
+    unsigned long long snap_gen = 0;
+    int snap_dev = -1;
+    i64 snap_w = 0, snap_h = 0;
 };
 
 struct NcrStaging {
@@ -190,6 +223,8 @@ struct NcrStaging {
 struct NcrContext {
     uint32_t magic = kMagicCtx;
     bool dead = false;
+    int dev = 0;              // the device this context lives on
+    unsigned long long gen = 1;   // bumped by everything that changes what the canvas will hold (recorded command, resize)
     i64 w = 0, h = 0;
     bool alpha = false;
     DevRef fb;
@@ -214,6 +249,11 @@ struct NcrContext {
     DevVec<unsigned char> d_yuv;
     bool u8_valid = false;
     bool yuv_valid = false;   // d_yuv holds the planes of the current canvas
+    // Present-only flushes (GetBufferAsUInt8 / YUV) do not write the f64 canvas back: a video frame's canvas is overwritten
+    // by the next frame's SetColor without ever being read (mil:866).  The canvas is then STALE: its true contents are
+    // "`last` applied to what fb holds"; anything that needs them re-runs `last` with write_fb = 1 first (materialize()).
+    bool fb_stale = false;
+    int elide_block = 0;      // > 0: this many coming present flushes write the canvas (the caller reads canvases between presents)
     uint32_t* h_cursors = nullptr;   // pinned, 8 words
     bool cursors_pending = false;
     cudaStream_t stream = nullptr;
@@ -244,6 +284,7 @@ inline NcrTexture* live(Texture* t) {
     return t;
 }
 inline int ipp_of(const NcrContext* c) { return c->alpha ? 4 : 3; }
+inline bool use_ctx(const NcrContext* c) { return set_device(c->dev); }
 
 void frame_dims(const NcrContext* c, NcrFrameDims* d) {
     d->w = (int32_t)c->w;
@@ -271,6 +312,7 @@ bool alloc_canvas(NcrContext* c, i64 w, i64 h) {
     c->u8_valid = false;
     c->yuv_valid = false;
     c->has_last = false;
+    c->fb_stale = false;
     return true;
 }
 
@@ -365,6 +407,41 @@ bool sync_ctx(NcrContext* c) {
     return !c->failed;
 }
 
+// Brings a stale canvas up to date: re-executes the resident last batch, this time writing the f64 canvas (no u8 / YUV output).
+// The batch's inputs are intact by construction — fb was not written, the command / list buffers are only replaced by the
+// next flush, and last_refs keeps its textures alive.
+bool env_flag(const char* name, bool dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    return atoi(v) != 0;
+}
+const bool kElidePresentWriteback = env_flag("NCR_ELIDE", true);
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+const int kPrefetchMode = env_int("NCR_PREFETCH", -1);
+const int kPrefetchMaxMean = env_int("NCR_PREFETCH_MAX_MEAN", 12);
+
+bool materialize(NcrContext* c) {
+    if (!c->fb_stale) return true;
+    c->fb_stale = false;
+    if (!c->has_last) return true;
+    NcrFlushArgs M = c->last;
+    M.u8_out = nullptr;
+    M.yuv_out = nullptr;
+    M.write_fb = 1;
+    M.count_pixels = 0;
+    ncr_launch_flush(&M, c->stream, nullptr);
+    g_launches += 3;
+    c->stats.kernel_launches += 3;
+    c->stats.materialized += 1;
+    c->last.write_fb = 1;
+    c->elide_block = 8;
+    if (!CK(cudaGetLastError())) { c->failed = true; return false; }
+    return true;
+}
+
 size_t yuv_bytes_of(const NcrContext* c) {
     return (size_t)c->w * c->h + 2 * (size_t)((c->w + 1) / 2) * (size_t)((c->h + 1) / 2);
 }
@@ -373,11 +450,14 @@ size_t yuv_bytes_of(const NcrContext* c) {
 // image in d_yuv (both fused into the composite's tile write-back).  With nothing pending, the outputs that are not
 // already current are produced from the canvas by the standalone kernels.
 bool flush(NcrContext* c, bool want_u8, bool want_yuv = false) {
-    if (!use_device()) return false;
+    if (!use_ctx(c)) return false;
     const size_t n_elems = (size_t)c->w * c->h * ipp_of(c);
     if (c->n == 0) {
         const bool need_yuv = want_yuv && !c->yuv_valid && n_elems;
-        if ((want_u8 || need_yuv) && !c->u8_valid && n_elems) {
+        const bool need_u8 = (want_u8 || need_yuv) && !c->u8_valid && n_elems;
+        // the canvas itself is wanted (no output requested) or an output has to be converted from it
+        if (c->fb_stale && ((!want_u8 && !want_yuv) || need_u8) && !materialize(c)) return false;
+        if (need_u8) {
             if (!c->d_u8.reserve(n_elems)) return false;
             ncr_launch_convert_u8((const double*)c->fb->p, c->d_u8.p, n_elems, c->stream);
             g_launches += 1;
@@ -397,14 +477,19 @@ bool flush(NcrContext* c, bool want_u8, bool want_yuv = false) {
         // results of the previous flush live in pinned words that the next one overwrites
         if (!sync_ctx(c)) return false;
     }
+    if (c->fb_stale) {
+        if (c->load_fb) { if (!materialize(c)) return false; }   // this batch reads the canvas
+        else c->fb_stale = false;                                // it starts with SetColor: the old contents are dead
+    }
     NcrFlushArgs A;
     memset(&A, 0, sizeof(A));
     frame_dims(c, &A.d);
     const size_t n_tiles = (size_t)A.d.tiles_x * A.d.tiles_y, n_bins = (size_t)A.d.bins_x * A.d.bins_y;
+    const size_t n_regions = n_tiles * NCR_REGIONS_PER_TILE;
     NcrStaging& S = c->stg[c->cur];
     bool ok = c->d_cmds.reserve(c->n) && c->d_boxes.reserve(c->n) && c->d_binbox.reserve(c->n) && c->d_aux.reserve(c->n_aux + 2) &&
               c->d_coarse.reserve(c->coarse_need + 1) && c->d_coarse_off.reserve(2 * n_bins) &&
-              c->d_fine.reserve(c->fine_need + 1) && c->d_fine_off.reserve(2 * n_tiles) && c->d_cursors.reserve(8);
+              c->d_fine.reserve(c->fine_need + 1) && c->d_fine_off.reserve(2 * n_regions) && c->d_cursors.reserve(8);
     if (ok && want_u8) ok = c->d_u8.reserve(n_elems);
     if (ok && want_yuv) ok = c->d_yuv.reserve(yuv_bytes_of(c));
     if (!ok) { c->failed = true; return false; }
@@ -436,6 +521,15 @@ bool flush(NcrContext* c, bool want_u8, bool want_yuv = false) {
     A.coarse_cap = (uint32_t)c->d_coarse.cap;
     A.fine_cap = (uint32_t)c->d_fine.cap;
     A.count_pixels = (c->stats_mode & 1) ? 1u : 0u;
+    // present-only flush: skip the canvas write-back unless this caller has been reading canvases between presents
+    bool elide = (want_u8 || want_yuv) && kElidePresentWriteback;
+    if (elide && c->elide_block > 0) { c->elide_block -= 1; elide = false; }
+    A.write_fb = elide ? 0u : 1u;
+    // Composite variant: with a handful of commands per region (chart / video frames) the per-region latency chain dominates
+    // and the cross-region prefetch variant pays; with long lists it only costs registers.  Decided from the host-side bound of
+    // the mean list length (NCR_PREFETCH=0/1 forces a variant; NCR_PREFETCH_MAX_MEAN moves the threshold).
+    A.prefetch = kPrefetchMode >= 0 ? (uint32_t)kPrefetchMode
+                                    : (c->fine_need <= (unsigned long long)kPrefetchMaxMean * n_regions ? 1u : 0u);
     const bool timed = (c->stats_mode & 2) != 0;
     ncr_launch_flush(&A, c->stream, timed ? c->ev : nullptr);
     g_launches += 3;
@@ -457,6 +551,7 @@ bool flush(NcrContext* c, bool want_u8, bool want_yuv = false) {
     c->load_fb = true;
     c->u8_valid = want_u8;
     c->yuv_valid = want_yuv;
+    c->fb_stale = elide;
     c->cur ^= 1;
     return true;
 }
@@ -464,14 +559,20 @@ bool flush(NcrContext* c, bool want_u8, bool want_yuv = false) {
 // Room for one more command (+ extra aux doubles) in the current staging buffers.
 bool reserve_cmd(NcrContext* c, size_t extra_aux) {
     NcrStaging& S = c->stg[c->cur];
+    // Recording normally touches no CUDA API.  The two cases that do (waiting for a staging buffer still being uploaded,
+    // growing pinned staging) first make the context's device current: a fresh worker thread's current device is 0, and
+    // an allocation made there would create a primary context on GPU 0 for every rank of a multi-GPU run.
     if (S.inflight) {
+        if (!use_ctx(c)) return false;
         cudaEventSynchronize(S.done);
         S.inflight = false;
     }
     if (c->n + 1 > S.cmds.cap) {
+        if (!use_ctx(c)) return false;
         if (!S.cmds.reserve(c->n + 1, c->n) || !S.boxes.reserve(S.cmds.cap, c->n) || !S.binbox.reserve(S.cmds.cap, c->n)) return false;
     }
     if (c->n_aux + extra_aux > S.aux.cap) {
+        if (!use_ctx(c)) return false;
         if (!S.aux.reserve(c->n_aux + extra_aux, c->n_aux)) return false;
     }
     return true;
@@ -514,7 +615,8 @@ NcrCmd* begin_cmd(NcrContext* c, uint32_t op, i64 l, i64 r, i64 t, i64 b, bool c
     if (c->st.ct[0] == 1.0 && c->st.ct[1] == 1.0 && c->st.ct[2] == 1.0) cmd->flags |= NCR_F_CT_RGB_ONE;
     NcrBox& bx = S.boxes.p[c->n];
     bx.l = cmd->l; bx.r = cmd->r; bx.t = cmd->t; bx.b = cmd->b;
-    const unsigned long long tx = ((r - 1) / NCR_TILE) - (l / NCR_TILE) + 1, ty = ((b - 1) / NCR_TILE) - (t / NCR_TILE) + 1;
+    // upper bound of the list entries this command can produce: one per 16x8 region its box touches
+    const unsigned long long tx = ((r - 1) / NCR_REGION_W) - (l / NCR_REGION_W) + 1, ty = ((b - 1) / NCR_REGION_H) - (t / NCR_REGION_H) + 1;
     const i64 edge = NCR_TILE * NCR_COARSE;
     if (l < r && t < b) {   // first / last bin touched, per axis (l < x1 <=> l/edge <= bin; r > x0 <=> (r-1)/edge >= bin)
         S.binbox.p[c->n] = (uint32_t)std::min<i64>(l / edge, 255) | ((uint32_t)std::min<i64>((r - 1) / edge, 255) << 8) |
@@ -526,6 +628,7 @@ NcrCmd* begin_cmd(NcrContext* c, uint32_t op, i64 l, i64 r, i64 t, i64 b, bool c
     c->fine_need += tx * ty;
     c->coarse_need += bxn * byn;
     c->n += 1;
+    c->gen += 1;
     return cmd;
 }
 
@@ -545,27 +648,56 @@ void put_const_colour(NcrContext* c, NcrCmd* cmd, double r, double g, double b, 
 
 bool is_pow2(i64 v) { return v > 0 && (v & (v - 1)) == 0; }
 
-// Texture operand of a draw.  Aliases of a canvas (cpp:377-384) are resolved to a snapshot of that canvas as of
-// this call, which is what an immediate-mode read of the shared buffer would have seen.
-// `keep` points at the reference that must outlive the recorded command: the texture's own buffer (no copy, hence no
-// atomic reference-count traffic on the draw path) or, for an alias, the snapshot stored in `snap_store`.
-bool bind_texture(NcrTexture* tex, const void** ptr, uint32_t* flags, DevRef* snap_store, const DevRef** keep) {
+// The texels of `tex` on device `dev`: the texture's own buffer, or a replica made (once) with a peer copy.  Returns a
+// pointer to a DevRef that stays where it is for the texture's lifetime (no shared_ptr copy — hence no contended atomic —
+// on the draw path).
+const DevRef* texels_on_device(NcrTexture* tex, int dev) {
+    if (dev == tex->dev) return &tex->buf;
+    if (dev < 0 || dev >= (int)tex->replicas.size()) return nullptr;
+    if (tex->replica_mask.load(std::memory_order_acquire) >> dev & 1ull) return &tex->replicas[dev];
+    std::lock_guard<std::mutex> lk(tex->mu);
+    if (tex->replica_mask.load(std::memory_order_acquire) >> dev & 1ull) return &tex->replicas[dev];
+    if (!set_device(dev)) return nullptr;
+    DevRef copy = dev_alloc(tex->buf->bytes);
+    if (!copy) return nullptr;
+    if (tex->buf->bytes && !CK(cudaMemcpyPeer(copy->p, dev, tex->buf->p, tex->dev, tex->buf->bytes))) return nullptr;
+    tex->replicas[dev] = copy;
+    tex->replica_mask.fetch_or(1ull << dev, std::memory_order_release);
+    return &tex->replicas[dev];
+}
+
+// Texture operand of a draw on device `dev`.  Aliases of a canvas (cpp:377-384) are resolved to a snapshot of that canvas
+// as of this call, which is what an immediate-mode read of the shared buffer would have seen; the snapshot is kept and
+// reused until the source context records something new (NcrContext::gen), so n draws of an unchanged shared canvas cost one
+// copy, not n.  An alias makes the drawing thread flush and read the SOURCE context: like every other use of one context
+// from two threads, that is only legal if the caller serialises them (threading).
+// `keep` receives the reference that must outlive the recorded command.
+bool bind_texture(int dev, NcrTexture* tex, const void** ptr, uint32_t* flags, const DevRef** keep) {
     if (tex->alias) {
         NcrContext* src = live(tex->alias);
         if (!src) return false;
-        if (!flush(src, false) || !sync_ctx(src)) return false;
-        const size_t bytes = (size_t)src->w * src->h * ipp_of(src) * sizeof(double);
-        DevRef snap = dev_alloc(bytes);
-        if (!snap) return false;
-        if (!CK(cudaMemcpy(snap->p, src->fb->p, bytes, cudaMemcpyDeviceToDevice))) return false;
-        *ptr = snap->p;
-        *snap_store = snap;
-        *keep = snap_store;
+        std::lock_guard<std::mutex> lk(tex->mu);
+        if (!tex->snap || tex->snap_gen != src->gen || tex->snap_dev != dev || tex->snap_w != src->w || tex->snap_h != src->h) {
+            if (!flush(src, false) || !sync_ctx(src)) return false;
+            if (!set_device(dev)) return false;
+            const size_t bytes = (size_t)src->w * src->h * ipp_of(src) * sizeof(double);
+            DevRef snap = dev_alloc(bytes);
+            if (!snap) return false;
+            if (bytes && !CK(cudaMemcpy(snap->p, src->fb->p, bytes, cudaMemcpyDefault))) return false;
+            tex->snap = snap;
+            tex->snap_gen = src->gen;
+            tex->snap_dev = dev;
+            tex->snap_w = src->w;
+            tex->snap_h = src->h;
+        }
+        *ptr = tex->snap->p;
+        *keep = &tex->snap;   // the caller copies it into the batch's references right away (keep_ref)
         *flags = NCR_F_TEX_F64 | (src->alpha ? NCR_F_TEX_ALPHA : 0);
         return true;
     }
-    *ptr = tex->buf->p;
-    *keep = &tex->buf;
+    *keep = texels_on_device(tex, dev);
+    if (!*keep || !**keep) return false;
+    *ptr = (**keep)->p;
     *flags = (tex->is_f64 ? NCR_F_TEX_F64 : 0) | (tex->alpha ? NCR_F_TEX_ALPHA : 0);
     return true;
 }
@@ -589,8 +721,10 @@ void keep_ref(NcrContext* c, const DevRef& r) {
     c->refs.push_back(r);
 }
 
-NcrTexture* new_texture(i64 w, i64 h, bool alpha, bool is_f64, const void* host_data) {
-    if (!use_device()) return nullptr;
+NcrTexture* new_texture(i64 w, i64 h, bool alpha, bool is_f64, const void* host_data, int dev = -1) {
+    if (!init_runtime()) return nullptr;
+    if (dev < 0) dev = g_dev;
+    if (!set_device(dev)) return nullptr;
     if (w < 0 || h < 0) { set_error("texture size", "negative"); return nullptr; }
     const size_t bytes = (size_t)w * h * (alpha ? 4 : 3) * (is_f64 ? 8 : 1);
     DevRef buf = dev_alloc(bytes);
@@ -598,19 +732,28 @@ NcrTexture* new_texture(i64 w, i64 h, bool alpha, bool is_f64, const void* host_
     if (host_data && bytes && !CK(cudaMemcpy(buf->p, host_data, bytes, cudaMemcpyHostToDevice))) return nullptr;
     NcrTexture* t = new NcrTexture();
     t->w = w; t->h = h; t->alpha = alpha; t->is_f64 = is_f64;
+    t->dev = dev;
     t->buf = buf;
+    t->replicas.resize((size_t)g_n_devices);
     return t;
 }
 
-// Materialises a texture operand for setup-time consumers (resample, hit-effect mask): alias -> snapshot.
-bool texture_view(NcrTexture* tex, NcrCmd* view, DevRef* keep) {
-    const DevRef* which = nullptr;
-    DevRef snap;
+// Materialises a texture operand for setup-time consumers (resample, hit-effect mask) on the device that holds it
+// (alias -> snapshot on the source canvas's device).  *dev_out receives that device.
+bool texture_view(NcrTexture* tex, NcrCmd* view, DevRef* keep, int* dev_out) {
     memset(view, 0, sizeof(*view));
     const void* p = nullptr;
     uint32_t flags = 0;
-    if (!bind_texture(tex, &p, &flags, &snap, &which)) return false;
+    int dev = tex->dev;
+    if (tex->alias) {
+        NcrContext* src = live(tex->alias);
+        if (!src) return false;
+        dev = src->dev;
+    }
+    const DevRef* which = nullptr;
+    if (!bind_texture(dev, tex, &p, &flags, &which)) return false;
     *keep = *which;
+    *dev_out = dev;
     i64 w, h;
     tex_dims(tex, &w, &h);
     view->tex = p;
@@ -632,11 +775,14 @@ long GetBufferSize(RenderContext* ctx) {
     return c ? c->w * c->h * ipp_of(c) : 0;
 }
 
-RenderContext* CreateRenderContext(long width, long height, bool enableAlpha) {
-    if (!use_device()) return nullptr;
+static RenderContext* create_context(long width, long height, bool enableAlpha, int dev) {
+    if (!init_runtime()) return nullptr;
+    if (dev < 0) dev = g_dev;
+    if (!set_device(dev)) return nullptr;
     NcrContext* c = new NcrContext();
     memset(&c->stats, 0, sizeof(c->stats));
     memset(&c->last, 0, sizeof(c->last));
+    c->dev = dev;
     c->alpha = enableAlpha;
     ncr_state_reset(c->st);
     bool ok = CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -654,9 +800,23 @@ RenderContext* CreateRenderContext(long width, long height, bool enableAlpha) {
     return c;
 }
 
+RenderContext* CreateRenderContext(long width, long height, bool enableAlpha) { return create_context(width, height, enableAlpha, -1); }
+
+RenderContext* NcrCreateRenderContextOnDevice(long width, long height, bool enableAlpha, int device) {
+    if (device < 0) { set_error("device index", "negative"); return nullptr; }
+    return create_context(width, height, enableAlpha, device);
+}
+
+int NcrDeviceCount(void) { return init_runtime() ? g_n_devices : 0; }
+
+int NcrContextDevice(RenderContext* ctx) {
+    NcrContext* c = live(ctx);
+    return c ? c->dev : -1;
+}
+
 void DestroyRenderContext(RenderContext* ctx) {
     NcrContext* c = live(ctx);
-    if (!c || !use_device()) return;
+    if (!c || !use_ctx(c)) return;
     cudaStreamSynchronize(c->stream);
     c->dead = true;
     g_live_contexts.fetch_sub(1, std::memory_order_relaxed);
@@ -682,10 +842,11 @@ void DestroyRenderContext(RenderContext* ctx) {
 
 void ResizeRenderContext(RenderContext* ctx, long width, long height) {
     NcrContext* c = live(ctx);
-    if (!c || !use_device()) return;
+    if (!c || !use_ctx(c)) return;
     // cpp:39-45: pixels are discarded, state is kept — pending draws can no longer be observed.
     cudaStreamSynchronize(c->stream);
     c->n = 0; c->n_aux = 0; c->coarse_need = c->fine_need = 0; c->load_fb = true;
+    c->gen += 1;
     c->refs.clear();
     alloc_canvas(c, width, height);
 }
@@ -904,7 +1065,7 @@ void DrawTexture(RenderContext* ctx, Texture* tex_, double x, double y, double w
     i64 tw, th;
     tex_dims(tex, &tw, &th);
     const double scaleX = tw / width, scaleY = th / height;   // cpp:728-729
-    const void* ptr; uint32_t tflags; DevRef snap; const DevRef* keep = nullptr;
+    const void* ptr; uint32_t tflags; const DevRef* keep = nullptr;
     if (ncr_is_no_transform(c->st.m)) {
         // cpp:741-742: for (i64 i = x; i < x + width; ++i) — the matrix is ignored, ApplyPixel clips.
         const i64 i0 = ncr_trunc_i64(x), j0 = ncr_trunc_i64(y);
@@ -914,7 +1075,7 @@ void DrawTexture(RenderContext* ctx, Texture* tex_, double x, double y, double w
         const i64 r = !(cr > 0) ? 0 : (cr >= (double)c->w ? c->w : (i64)cr);
         const i64 b = !(cb > 0) ? 0 : (cb >= (double)c->h ? c->h : (i64)cb);
         if (l >= r || t >= b) return;
-        if (!bind_texture(tex, &ptr, &tflags, &snap, &keep)) return;
+        if (!bind_texture(c->dev, tex, &ptr, &tflags, &keep)) return;
         NcrCmd* cmd = begin_cmd(c, NCR_OP_TEX_IDENT, l, r, t, b);
         if (!cmd) return;
         fill_texture_fields(c, cmd, ptr, tflags, *keep, tw, th);
@@ -926,7 +1087,7 @@ void DrawTexture(RenderContext* ctx, Texture* tex_, double x, double y, double w
     i64 l, r, t, b;
     ncr_border(c->st.m, x, y, width, height, c->w, c->h, &l, &r, &t, &b);
     if (l >= r || t >= b) return;
-    if (!bind_texture(tex, &ptr, &tflags, &snap, &keep)) return;
+    if (!bind_texture(c->dev, tex, &ptr, &tflags, &keep)) return;
     NcrCmd* cmd = begin_cmd(c, NCR_OP_TEX, l, r, t, b);
     if (!cmd) return;
     fill_texture_fields(c, cmd, ptr, tflags, *keep, tw, th);
@@ -946,8 +1107,8 @@ void DrawSplittedTexture(RenderContext* ctx, Texture* tex_, double x, double y, 
     i64 l, r, t, b;
     ncr_border(c->st.m, x, y, width, height, c->w, c->h, &l, &r, &t, &b);
     if (l >= r || t >= b) return;
-    const void* ptr; uint32_t tflags; DevRef snap; const DevRef* keep = nullptr;
-    if (!bind_texture(tex, &ptr, &tflags, &snap, &keep)) return;
+    const void* ptr; uint32_t tflags; const DevRef* keep = nullptr;
+    if (!bind_texture(c->dev, tex, &ptr, &tflags, &keep)) return;
     NcrCmd* cmd = begin_cmd(c, NCR_OP_TEX_SPLIT, l, r, t, b);
     if (!cmd) return;
     fill_texture_fields(c, cmd, ptr, tflags, *keep, tw, th);
@@ -1092,7 +1253,7 @@ Texture* CreateTextureFromRenderContext(RenderContext* ctx) {
     NcrContext* c = live(ctx);
     if (!c) return nullptr;
     if (!flush(c, false)) return nullptr;
-    NcrTexture* t = new_texture(c->w, c->h, c->alpha, true, nullptr);
+    NcrTexture* t = new_texture(c->w, c->h, c->alpha, true, nullptr, c->dev);
     if (!t) return nullptr;
     const size_t bytes = (size_t)c->w * c->h * ipp_of(c) * sizeof(double);
     if (bytes && !CK(cudaMemcpyAsync(t->buf->p, c->fb->p, bytes, cudaMemcpyDeviceToDevice, c->stream))) return nullptr;
@@ -1105,6 +1266,7 @@ Texture* CreateTextureFromRenderContextShared(RenderContext* ctx) {
     if (!c) return nullptr;
     NcrTexture* t = new NcrTexture();
     t->w = c->w; t->h = c->h; t->alpha = c->alpha; t->is_f64 = true;
+    t->dev = c->dev;
     t->alias = c;
     return t;
 }
@@ -1132,17 +1294,20 @@ bool GetTextureEnableAlpha(Texture* tex_) {
 
 Texture* ResampleTexture(Texture* tex_, long width, long height) {
     NcrTexture* tex = live(tex_);
-    if (!tex || !use_device()) return nullptr;
+    if (!tex || !init_runtime()) return nullptr;
     NcrCmd view;
     DevRef keep;
-    if (!texture_view(tex, &view, &keep)) return nullptr;
+    int dev = 0;
+    if (!texture_view(tex, &view, &keep, &dev)) return nullptr;
     const bool f64 = (view.flags & NCR_F_TEX_F64) != 0, alpha = (view.flags & NCR_F_TEX_ALPHA) != 0;
-    NcrTexture* out = new_texture(width, height, alpha, f64, nullptr);
+    NcrTexture* out = new_texture(width, height, alpha, f64, nullptr, dev);   // leaves `dev` current
     if (!out) return nullptr;
     if (width > 0 && height > 0) {
-        ncr_launch_resample(&view, out->buf->p, (int)width, (int)height, 0);
+        // The calling thread's own stream: it does not serialise with the legacy default stream or with any context's
+        // (non-blocking) stream; the source texels were written by synchronous copies, so they are visible.
+        ncr_launch_resample(&view, out->buf->p, (int)width, (int)height, cudaStreamPerThread);
         g_launches += 1;
-        if (!CK(cudaGetLastError()) || !CK(cudaStreamSynchronize(0))) return nullptr;
+        if (!CK(cudaGetLastError()) || !CK(cudaStreamSynchronize(cudaStreamPerThread))) return nullptr;
     }
     return out;
 }
@@ -1153,23 +1318,28 @@ void GetMilthmHitEffectPixel(double seed, double t, double x, double y, double* 
 
 Texture* CreateMilthmHitEffectTexture(Texture* mask_, double seed, double t, double r, double g, double b) {
     NcrTexture* mask = live(mask_);
-    if (!mask || !use_device()) return nullptr;
+    if (!mask || !init_runtime()) return nullptr;
     if (!mask->alpha) return nullptr;   // cpp:1418
-    const i64 w = mask->w, h = mask->h;
+    i64 w, h;
+    tex_dims(mask, &w, &h);   // an alias follows its canvas through ResizeRenderContext
     const size_t n = (size_t)w * h;
     // The noise uses libm sin/atan2 (cpp:1339-1389) and is thresholded, so it is evaluated on the host to stay
     // bit-identical; only the mask's alpha plane is needed from the device (fetched once per mask).
     std::vector<double> mask_a(n);
     if (mask->alias || mask->is_f64) {
         NcrCmd view; DevRef keep;
-        if (!texture_view(mask, &view, &keep)) return nullptr;
+        int vdev = 0;
+        if (!texture_view(mask, &view, &keep, &vdev) || !set_device(vdev)) return nullptr;
         std::vector<double> all(n * 4);
         if (n && !CK(cudaMemcpy(all.data(), view.tex, n * 4 * sizeof(double), cudaMemcpyDeviceToHost))) return nullptr;
         for (size_t k = 0; k < n; ++k) mask_a[k] = all[4 * k + 3];
     } else {
+        std::lock_guard<std::mutex> lk(mask->mu);   // one mask is shared by every effect texture built from it, possibly from several threads
         if (mask->shadow.size() != n * 4) {
-            mask->shadow.resize(n * 4);
-            if (n && !CK(cudaMemcpy(mask->shadow.data(), mask->buf->p, n * 4, cudaMemcpyDeviceToHost))) return nullptr;
+            if (!set_device(mask->dev)) return nullptr;
+            std::vector<unsigned char> fetched(n * 4);
+            if (n && !CK(cudaMemcpy(fetched.data(), mask->buf->p, n * 4, cudaMemcpyDeviceToHost))) return nullptr;
+            mask->shadow.swap(fetched);
         }
         for (size_t k = 0; k < n; ++k) mask_a[k] = mask->shadow[4 * k + 3] / 255.0;
     }
@@ -1235,8 +1405,21 @@ int NcrFlush(RenderContext* ctx) {
     return sync_ctx(c) ? 0 : -1;
 }
 
-const char* NcrLastError(void) { return g_err; }
-const char* NcrDeviceName(void) { return g_devname; }
+// The text is copied under the lock that writers hold into a buffer owned by the calling thread, so a reader never sees a
+// half-written message and the returned pointer stays valid until this thread's next call.
+const char* NcrLastError(void) {
+    static thread_local char copy[sizeof(g_err)];
+    std::lock_guard<std::mutex> lk(g_mu);
+    memcpy(copy, g_err, sizeof(copy));
+    return copy;
+}
+
+const char* NcrDeviceName(void) {
+    static thread_local char copy[256];
+    std::lock_guard<std::mutex> lk(g_mu);
+    snprintf(copy, sizeof(copy), "%s", g_dev >= 0 ? g_devname[g_dev] : "");
+    return copy;
+}
 
 void* NcrAllocHost(unsigned long long bytes) {
     if (!use_device()) return nullptr;
@@ -1252,7 +1435,7 @@ void NcrFreeHost(void* p) {
 void NcrGetStats(RenderContext* ctx, NcrStats* out) {
     NcrContext* c = live(ctx);
     if (!c || !out) return;
-    if (use_device()) sync_ctx(c);
+    if (use_ctx(c)) sync_ctx(c);
     *out = c->stats;
 }
 
@@ -1269,18 +1452,21 @@ double NcrMeasureF64Rate(void) {
     return ncr_measure_f64_rate(0);
 }
 
-int NcrRerunLastFlush(RenderContext* ctx, int iters, int flush_l2, float* ms_out) {
+int NcrRerunLastFlushEx(RenderContext* ctx, int iters, int flush_l2, float* ms_out, int write_fb, int prefetch) {
     NcrContext* c = live(ctx);
-    if (!c || !c->has_last || !use_device()) return -1;
+    if (!c || !c->has_last || !use_ctx(c)) return -1;
     if (!sync_ctx(c)) return -1;
-    if (flush_l2 && !g_l2_scrub) {
+    if (flush_l2 && !g_l2_scrub[c->dev]) {
         std::lock_guard<std::mutex> lk(g_mu);
-        if (!g_l2_scrub && cudaMalloc(&g_l2_scrub, kL2ScrubBytes) != cudaSuccess) return -1;
+        if (!g_l2_scrub[c->dev] && cudaMalloc(&g_l2_scrub[c->dev], kL2ScrubBytes) != cudaSuccess) return -1;
     }
+    NcrFlushArgs R = c->last;
+    if (write_fb >= 0) R.write_fb = write_fb ? 1u : 0u;
+    if (prefetch >= 0) R.prefetch = prefetch ? 1u : 0u;
     for (int it = 0; it < iters; ++it) {
-        if (flush_l2) cudaMemsetAsync(g_l2_scrub, it & 0xff, kL2ScrubBytes, c->stream);
+        if (flush_l2) cudaMemsetAsync(g_l2_scrub[c->dev], it & 0xff, kL2ScrubBytes, c->stream);
         cudaEventRecord(c->ev_t0, c->stream);
-        ncr_launch_flush(&c->last, c->stream, c->ev);
+        ncr_launch_flush(&R, c->stream, c->ev);
         cudaEventRecord(c->ev_t1, c->stream);
         g_launches += 3;
         c->stats.kernel_launches += 3;
@@ -1293,9 +1479,14 @@ int NcrRerunLastFlush(RenderContext* ctx, int iters, int flush_l2, float* ms_out
             cudaEventElapsedTime(&o[3], c->ev[2], c->ev[3]);   // ncr_composite
         }
     }
+    if (iters > 0 && R.write_fb) { c->fb_stale = false; c->last.write_fb = 1; }   // the canvas now holds the batch's result
     c->u8_valid = c->last.u8_out != nullptr;
     c->yuv_valid = c->last.yuv_out != nullptr;
     return 0;
+}
+
+int NcrRerunLastFlush(RenderContext* ctx, int iters, int flush_l2, float* ms_out) {
+    return NcrRerunLastFlushEx(ctx, iters, flush_l2, ms_out, -1, -1);
 }
 
 void NcrSetClipRect(RenderContext* ctx, long x, long y, long width, long height) {
@@ -1332,8 +1523,8 @@ void NcrDrawTexturePerspective(RenderContext* ctx, Texture* tex_, const double i
     if (width == 0 || height == 0) return;
     i64 tw, th;
     tex_dims(tex, &tw, &th);
-    const void* ptr; uint32_t tflags; DevRef snap; const DevRef* keep = nullptr;
-    if (!bind_texture(tex, &ptr, &tflags, &snap, &keep)) return;
+    const void* ptr; uint32_t tflags; const DevRef* keep = nullptr;
+    if (!bind_texture(c->dev, tex, &ptr, &tflags, &keep)) return;
     // Pixel box: forward-map the source rectangle through the inverse of inv_h (a projective map keeps the rectangle's
     // image inside the hull of its corners as long as the homogeneous w stays positive on it), pad, and fall back to the
     // whole canvas whenever that cannot be trusted (singular / ill-conditioned matrix, w <= 0 at a corner, non-finite).

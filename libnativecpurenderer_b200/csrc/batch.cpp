@@ -68,13 +68,15 @@ extern "C" {
 
 // Contexts, their device buffers and the pinned frame buffers are created once and reused by every render call
 // (cudaMalloc / cudaFree synchronise the device: they must not sit inside a render).
-NcrFramePool* NcrCreateFramePool(long width, long height, int alpha, int n_workers) {
+NcrFramePool* NcrCreateFramePoolOnDevices(long width, long height, int alpha, int n_workers, const int* devices, int n_devices) {
     if (width <= 0 || height <= 0) return nullptr;
-    n_workers = std::max(1, std::min(n_workers, 64));
+    n_workers = std::max(1, std::min(n_workers, 256));
     NcrFramePool* p = new NcrFramePool();
     p->width = width; p->height = height; p->alpha = alpha;
     for (int k = 0; k < n_workers; ++k) {
-        RenderContext* c = CreateRenderContext(width, height, alpha != 0);
+        // worker k -> device devices[k % n_devices]: consecutive frames go to different GPUs, so the in-order sink drains them evenly
+        RenderContext* c = (devices && n_devices > 0) ? NcrCreateRenderContextOnDevice(width, height, alpha != 0, devices[k % n_devices])
+                                                      : CreateRenderContext(width, height, alpha != 0);
         if (!c) break;
         p->u8_bytes = GetBufferSize(c);
         p->yuv_bytes = NcrYUV420PSize(c);
@@ -88,6 +90,10 @@ NcrFramePool* NcrCreateFramePool(long width, long height, int alpha, int n_worke
     }
     if (p->ctx.empty()) { delete p; return nullptr; }
     return p;
+}
+
+NcrFramePool* NcrCreateFramePool(long width, long height, int alpha, int n_workers) {
+    return NcrCreateFramePoolOnDevices(width, height, alpha, std::min(n_workers, 64), nullptr, 0);
 }
 
 void NcrDestroyFramePool(NcrFramePool* p) {

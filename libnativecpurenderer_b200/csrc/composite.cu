@@ -8,8 +8,9 @@
 //
 // Per command the warp stages the 240-byte command in a per-warp shared slot (the next one is fetched while the
 // current one is applied), reads its parameters as warp-uniform LDS broadcasts and amortises them over its 128
-// pixels; commands that provably miss the half-tile are rejected exactly during the list walk.  Texel fetches of
-// the four pixels are issued back to back before any is consumed.  The write-back produces, in the same pass, the
+// pixels.  The region's list (written by ncr_bin_fine) holds only commands that can touch the region, each tagged
+// INTERIOR when every pixel of the region provably passes its box and coverage tests: those run straight-line code
+// with no per-pixel test or select on coverage.  Texel fetches of the four pixels are issued back to back before any is consumed.  The write-back produces, in the same pass, the
 // f64 canvas and — when asked — the (iu8)(v*255) image or its YUV 4:2:0 planes (present path).
 //
 // Arithmetic: the reference's f64 expression trees (reference src/libNativeCPURenderer.cpp, cited inline),
@@ -46,6 +47,7 @@ __device__ __noinline__ double ncr_sqrt(double a) { return __dsqrt_rn(a); }
 #ifndef NCR_NY
 #define NCR_NY 2
 #endif
+static_assert(NCR_NX == 2 && NCR_NY == 2, "ncr_bin_fine writes lists for 16x8 regions: 4 pixel slots per lane");
 #define NCR_RH (4 * NCR_NY)                      // region height in pixels
 #define NCR_P (NCR_NX * NCR_NY)
 #define NCR_RW (8 * NCR_NX)                      // region width in pixels
@@ -197,33 +199,6 @@ __device__ __forceinline__ bool any_slot(const bool (&in)[NCR_P]) {
     return r;
 }
 
-// Exact rejection of a command against a block of pixels [i0,i1] x [j0,j1] (inclusive), for the ops whose coverage is the
-// four inclusive bounds of cpp:765-768 on the inverse-mapped position.
-//
-// X(i,j) = fl(fl(fl(inv0*i) + fl(inv2*j)) + inv4) is monotone in i and in j separately (IEEE rounding is monotone), so its
-// maximum and minimum over the block are attained at block corners chosen by the signs of inv0 and inv2.  Evaluating the
-// SAME expression at those corners therefore bounds the value every pixel of the block will compute: if max X < x, every
-// pixel fails `invX < x -> continue`, and likewise for the other three bounds.  No tolerance is involved; a NaN bound
-// compares false and never rejects.
-__device__ __forceinline__ bool quad_misses_region(const NcrCmd* __restrict__ c, int i0, int i1, int j0, int j1) {
-    const uint32_t op = __ldg(&c->op);
-    if (op != NCR_OP_TEX && op != NCR_OP_TEX_SPLIT && op != NCR_OP_RECT && op != NCR_OP_GRAD) return false;
-    const double2 m01 = __ldg((const double2*)&c->inv[0]), m23 = __ldg((const double2*)&c->inv[2]);
-    const double2 m45 = __ldg((const double2*)&c->inv[4]);
-    const double2 lo = __ldg((const double2*)&c->x), hi = __ldg((const double2*)&c->xw);
-    const double fi0 = (double)i0, fi1 = (double)i1, fj0 = (double)j0, fj1 = (double)j1;
-    // X = (inv0*i + inv2*j) + inv4
-    const double xa_hi = MUL(m01.x, m01.x >= 0.0 ? fi1 : fi0), xa_lo = MUL(m01.x, m01.x >= 0.0 ? fi0 : fi1);
-    const double xb_hi = MUL(m23.x, m23.x >= 0.0 ? fj1 : fj0), xb_lo = MUL(m23.x, m23.x >= 0.0 ? fj0 : fj1);
-    const double x_max = ADD(ADD(xa_hi, xb_hi), m45.x), x_min = ADD(ADD(xa_lo, xb_lo), m45.x);
-    // Y = (inv1*i + inv3*j) + inv5
-    const double ya_hi = MUL(m01.y, m01.y >= 0.0 ? fi1 : fi0), ya_lo = MUL(m01.y, m01.y >= 0.0 ? fi0 : fi1);
-    const double yb_hi = MUL(m23.y, m23.y >= 0.0 ? fj1 : fj0), yb_lo = MUL(m23.y, m23.y >= 0.0 ? fj0 : fj1);
-    const double y_max = ADD(ADD(ya_hi, yb_hi), m45.y), y_min = ADD(ADD(ya_lo, yb_lo), m45.y);
-    return x_max < lo.x || x_min > hi.x || y_max < lo.y || y_min > hi.y;
-}
-
-
 // Per-lane pixel slots of the current half-tile.
 struct Slots {
     int xs[NCR_NX], ys[NCR_NY];        // pixel columns / rows owned by this lane
@@ -302,7 +277,9 @@ __device__ __forceinline__ void shade_bilinear_rgba8(const NcrCmd& c, uint32_t l
 // Fast path of the two hot ops — DrawTexture (inverse-mapped, cpp:753-778) and DrawSplittedTexture (cpp:781-820) on
 // RGBA8 textures with nearest sampling.  Written as straight-line code over the four pixel slots (no branch between
 // slots), so the f64 dependency chains of the slots interleave.
-template <bool ALPHA, bool COUNT>
+// INTERIOR: ncr_bin_fine proved that every pixel of the region passes the box and the four bounds: `in` is constant true, the
+// bounds are not evaluated and every select on coverage folds away.
+template <bool ALPHA, bool COUNT, bool INTERIOR>
 __device__ __forceinline__ void tex_fast(const NcrCmd& c, const uint32_t op, const uint32_t flags, const Slots& S,
                                          const double* lut, uint32_t lut_base, bool (&in)[NCR_P], double (&dr)[NCR_P], double (&dg)[NCR_P],
                                          double (&db)[NCR_P], double (&da)[NCR_P], unsigned long long& n_applied) {
@@ -320,11 +297,11 @@ __device__ __forceinline__ void tex_fast(const NcrCmd& c, const uint32_t op, con
         const double X = ADD(ADD(ax[SX(p)], ay[SY(p)]), i4);
         const double Y = ADD(ADD(bx[SX(p)], by[SY(p)]), i5);
         // the four inclusive bounds, cpp:765-768 (NaN compares false on both sides, as in C)
-        in[p] = in[p] && !(X < cx) && !(X > cxw) && !(Y < cy) && !(Y > cyh);
+        if (!INTERIOR) in[p] = in[p] && !(X < cx) && !(X > cxw) && !(Y < cy) && !(Y > cyh);
         u[p] = MUL(SUB(X, cx), sx);   // cpp:770-771
         v[p] = MUL(SUB(Y, cy), sy);
     }
-    if (!__any_sync(FULL, any_slot(in))) return;
+    if (!INTERIOR && !__any_sync(FULL, any_slot(in))) return;
     if (op == NCR_OP_TEX_SPLIT) {
         // cpp:812-813: u = (uStart + (uEnd - uStart) * u / tex->width) * tex->width
         const double uS = c.p[0], dU = c.p[1], vS = c.p[2], dV = c.p[3], fw = c.p[4], fh = c.p[5];
@@ -347,10 +324,67 @@ __device__ __forceinline__ void tex_fast(const NcrCmd& c, const uint32_t op, con
         // reference reads out of bounds there).  min + relu is one VIMNMX.
         const int xi = __vimin_s32_relu(__double2int_rz(u[p]), tw2);
         const int yi = __vimin_s32_relu(__double2int_rz(v[p]), th2);
-        tx[p] = in[p] ? __ldg(t32 + (yi * tw + xi)) : 0u;
+        tx[p] = (INTERIOR || in[p]) ? __ldg(t32 + (yi * tw + xi)) : 0u;
     }
     if (flags & NCR_F_CT_RGB_ONE) shade_rgba8<ALPHA, COUNT, true>(c, lut_base, tx, in, dr, dg, db, da, n_applied);
     else shade_rgba8<ALPHA, COUNT, false>(c, lut_base, tx, in, dr, dg, db, da, n_applied);
+}
+
+// A command tagged INTERIOR by ncr_bin_fine: every pixel of the region is inside the command's box and passes its coverage
+// test, so the common ops run without any per-pixel test and without selects on coverage (the arithmetic per pixel is the
+// same as in apply_cmd — only `in` is the constant true).  Returns false (warp-uniform) for ops that have no interior
+// variant; the caller then runs apply_cmd, which is always correct.
+template <bool ALPHA, bool COUNT>
+__device__ __forceinline__ bool apply_interior(const NcrCmd& c, const Slots& S, const double* lut, uint32_t lut_base,
+                                               double (&dr)[NCR_P], double (&dg)[NCR_P], double (&db)[NCR_P], double (&da)[NCR_P],
+                                               unsigned long long& n_applied) {
+    const uint32_t op = c.op, flags = c.flags;
+    bool in[NCR_P];
+    FOR4 in[p] = true;
+    if (flags & NCR_F_FAST_AFFINE) {
+        tex_fast<ALPHA, COUNT, true>(c, op, flags, S, lut, lut_base, in, dr, dg, db, da, n_applied);
+        return true;
+    }
+    if (op == NCR_OP_FILL_COLOR || op == NCR_OP_RECT) {   // constant colour, see apply_cmd
+        const double sa = c.p[3];
+        if (sa != 1.0) {
+            const double q0 = c.p[4], q1 = c.p[5], q2 = c.p[6], om = c.p[7];
+            FOR4 {
+                dr[p] = ADD(MUL(dr[p], om), q0); dg[p] = ADD(MUL(dg[p], om), q1); db[p] = ADD(MUL(db[p], om), q2);
+                if (ALPHA) da[p] = sa;
+            }
+        } else {
+            FOR4 {
+                dr[p] = c.p[0]; dg[p] = c.p[1]; db[p] = c.p[2];
+                if (ALPHA) da[p] = sa;
+            }
+        }
+        if (COUNT) n_applied += NCR_P;
+        return true;
+    }
+    if (op == NCR_OP_SET_COLOR && !(flags & NCR_F_RGB_SPILL)) {   // cpp:643-657
+        FOR4 {
+            dr[p] = c.p[0]; dg[p] = c.p[1]; db[p] = c.p[2];
+            if (ALPHA) da[p] = c.p[3];
+        }
+        return true;
+    }
+    if (op == NCR_OP_TEX_IDENT && (flags & NCR_F_TEX_FAST)) {   // cpp:741-751 on RGBA8 texels
+        const double cx = c.x, cy = c.y, sx = c.sx, sy = c.sy;
+        const int tw = c.tex_w, tw2 = tw - 2, th2 = c.tex_h - 2;
+        const uint32_t* t32 = (const uint32_t*)c.tex;
+        int xi[NCR_NX], yi[NCR_NY];
+#pragma unroll
+        for (int k = 0; k < NCR_NX; ++k) xi[k] = __vimin_s32_relu(__double2int_rz(MUL(SUB(S.fx[k], cx), sx)), tw2);
+#pragma unroll
+        for (int k = 0; k < NCR_NY; ++k) yi[k] = __vimin_s32_relu(__double2int_rz(MUL(SUB(S.fy[k], cy), sy)), th2) * tw;
+        uint32_t tx[NCR_P];
+        FOR4 tx[p] = __ldg(t32 + (yi[SY(p)] + xi[SX(p)]));
+        if (flags & NCR_F_CT_RGB_ONE) shade_rgba8<ALPHA, COUNT, true>(c, lut_base, tx, in, dr, dg, db, da, n_applied);
+        else shade_rgba8<ALPHA, COUNT, false>(c, lut_base, tx, in, dr, dg, db, da, n_applied);
+        return true;
+    }
+    return false;
 }
 
 // One command applied to the warp's 128 pixels.  `c` lives in shared memory (warp-uniform reads: one wavefront each).
@@ -372,7 +406,7 @@ __device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A
     FOR4 in[p] = inx[SX(p)] && iny[SY(p)];
 
     if (flags & NCR_F_FAST_AFFINE) {   // DrawTexture / DrawSplittedTexture on RGBA8, nearest: the hot case, tested first
-        tex_fast<ALPHA, COUNT>(c, op, flags, S, lut, lut_base, in, dr, dg, db, da, n_applied);
+        tex_fast<ALPHA, COUNT, false>(c, op, flags, S, lut, lut_base, in, dr, dg, db, da, n_applied);
         return;
     }
 
@@ -536,13 +570,163 @@ __device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A
     }
 }
 
+// Copies command `e` (list entry) from HBM into a per-warp shared slot: 15 lanes x 16 bytes.
+__device__ __forceinline__ void stage_cmd(const NcrFlushArgs& A, NcrCmd* dst, uint32_t e, int lane) {
+    constexpr uint32_t WORDS = NCR_CMD_WORDS16;   // 15 x 16 B
+    if (lane < (int)WORDS) ((uint4*)dst)[lane] = __ldg((const uint4*)(A.cmds + (e & NCR_ENTRY_INDEX)) + lane);
+    __syncwarp();
+}
+
+// One region (16x8 px) composited by one warp: pixel set-up, optional canvas read, the region's command list in submission
+// order, write-back (f64 canvas unless write_fb == 0, fused u8 image, fused YUV planes).
+//   ents       the first 32 entries of the region's list, one per lane (already loaded);
+//   slot       in/out: which of the warp's two shared command slots holds the command to run next;
+//   have_cmd0  the region's first command is already staged in s_cmd[slot] (cross-region prefetch);
+//   next_valid / next_e0   cross-region prefetch: the first list entry of the region this warp composites next; its command is
+//              fetched while this region's last command is applied.  Returns true when that command is staged in s_cmd[slot].
 template <bool ALPHA, bool COUNT>
+__device__ __forceinline__ bool run_region(const NcrFlushArgs& A, NcrCmd (*s_cmd)[2], const int task, const uint32_t loff,
+                                           const uint32_t lcount, uint32_t ents, int& slot, const bool have_cmd0,
+                                           const bool next_valid, const uint32_t next_e0, const double* lut,
+                                           unsigned long long& n_applied) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t lut_base = (uint32_t)lane * 8u;
+    const int lx = lane & 7, ly = lane >> 3;
+    constexpr int IPP = ALPHA ? 4 : 3;
+    constexpr uint32_t WORDS = NCR_CMD_WORDS16;
+    const int W = A.d.w, H = A.d.h;
+    const uint32_t* __restrict__ list = A.fine_list;
+    const int tile = task / NCR_TASKS_PER_TILE, sub = task % NCR_TASKS_PER_TILE;
+    const int x0 = (tile % A.d.tiles_x) * NCR_TILE + (sub % (16 / NCR_RW)) * NCR_RW;
+    const int y0 = (tile / A.d.tiles_x) * NCR_TILE + (sub / (16 / NCR_RW)) * NCR_RH;
+    if ((lcount == 0 && A.u8_out == nullptr && A.yuv_out == nullptr) || y0 >= H || x0 >= W) {   // nothing to do here
+        if (next_valid) stage_cmd(A, &s_cmd[0][slot], next_e0, lane);
+        return next_valid;
+    }
+    Slots S;
+#pragma unroll
+    for (int k = 0; k < NCR_NX; ++k) { S.xs[k] = x0 + 8 * k + lx; S.fx[k] = (double)S.xs[k]; }
+#pragma unroll
+    for (int k = 0; k < NCR_NY; ++k) { S.ys[k] = y0 + 4 * k + ly; S.fy[k] = (double)S.ys[k]; }
+    bool valid[NCR_P];
+    FOR4 valid[p] = S.xs[SX(p)] < W && S.ys[SY(p)] < H;
+
+    double dr[NCR_P], dg[NCR_P], db[NCR_P], da[NCR_P];
+    FOR4 { dr[p] = 0.0; dg[p] = 0.0; db[p] = 0.0; da[p] = 0.0; }
+    // The canvas is read unless the list starts with a SetColor (then every pixel is overwritten first).
+    if (A.load_fb != 0 || lcount == 0) {
+        FOR4 if (valid[p]) {
+            const double* q = A.fb + ((size_t)S.ys[SY(p)] * W + S.xs[SX(p)]) * IPP;
+            if (ALPHA) {
+                const double2 lo = ((const double2*)q)[0], hi = ((const double2*)q)[1];
+                dr[p] = lo.x; dg[p] = lo.y; db[p] = hi.x; da[p] = hi.y;
+            } else {
+                dr[p] = q[0]; dg[p] = q[1]; db[p] = q[2];
+            }
+        }
+    }
+
+    // Walk the region's list in submission order.  Every entry is a command to run (ncr_bin_fine did the culling); the
+    // next command — at the end of the list, the first command of the warp's next region — is fetched into the other
+    // shared slot while the current one is applied.
+    uint32_t cur = __shfl_sync(FULL, ents, 0);
+    if (lcount != 0 && !have_cmd0) stage_cmd(A, &s_cmd[0][slot], cur, lane);
+    bool staged_next = false;
+    if (lcount == 0 && next_valid) { stage_cmd(A, &s_cmd[0][slot], next_e0, lane); staged_next = true; }
+    for (uint32_t k = 0; k < lcount; ++k) {
+        const bool more = k + 1 < lcount;
+        uint32_t nxt = next_e0;
+        if (more) {
+            if (((k + 1) & 31u) == 0u) ents = (k + 1 + lane < lcount) ? __ldg(list + loff + k + 1 + lane) : 0u;   // next 32 entries
+            nxt = __shfl_sync(FULL, ents, (k + 1) & 31);
+        }
+        const bool fetch = more || next_valid;
+        uint4 pre = make_uint4(0, 0, 0, 0);
+        if (fetch && lane < (int)WORDS) pre = __ldg((const uint4*)(A.cmds + (nxt & NCR_ENTRY_INDEX)) + lane);   // in flight during the apply
+        const NcrCmd& c = s_cmd[0][slot];
+        if (!(cur & NCR_ENTRY_INTERIOR) || !apply_interior<ALPHA, COUNT>(c, S, lut, lut_base, dr, dg, db, da, n_applied))
+            apply_cmd<ALPHA, COUNT>(c, A, S, lut, lut_base, dr, dg, db, da, n_applied);
+        if (fetch && lane < (int)WORDS) ((uint4*)&s_cmd[0][slot ^ 1])[lane] = pre;
+        __syncwarp();
+        if (fetch) slot ^= 1;
+        if (!more) staged_next = next_valid;
+        cur = nxt;
+    }
+
+    // region write-back: canonical f64 canvas (only if something was drawn, and not for a present-only flush) and the fused (iu8)(v*255) image
+    FOR4 if (valid[p]) {
+        const size_t pix = ((size_t)S.ys[SY(p)] * W + S.xs[SX(p)]) * IPP;
+        if (lcount != 0 && A.write_fb) {
+            double* q = A.fb + pix;
+            if (ALPHA) {
+                ((double2*)q)[0] = make_double2(dr[p], dg[p]);
+                ((double2*)q)[1] = make_double2(db[p], da[p]);
+            } else {
+                q[0] = dr[p]; q[1] = dg[p]; q[2] = db[p];
+            }
+        }
+        if (A.u8_out) {
+            if (ALPHA) {
+                const uint32_t o = (uint32_t)ncr_to_u8(dr[p]) | ((uint32_t)ncr_to_u8(dg[p]) << 8) |
+                                   ((uint32_t)ncr_to_u8(db[p]) << 16) | ((uint32_t)ncr_to_u8(da[p]) << 24);
+                ((uint32_t*)A.u8_out)[(size_t)S.ys[SY(p)] * W + S.xs[SX(p)]] = o;
+            } else {
+                unsigned char* o = A.u8_out + pix;
+                o[0] = ncr_to_u8(dr[p]); o[1] = ncr_to_u8(dg[p]); o[2] = ncr_to_u8(db[p]);
+            }
+        }
+    }
+    // Present path, fused: the YUV 4:2:0 planes of the (iu8)(v*255) image, same arithmetic as ncr_yuv420p
+    // (kernels.cu).  A 2x2 chroma block is (lane, lane^1) x (lane, lane^8) of the same pixel slot — region origins are
+    // even — so the block sums are two shuffles of the packed 10-bit channel sums; a missing neighbour column / row
+    // (odd canvas size) is replaced by the pixel's own, which is the edge replication of the standalone kernel.
+    if (A.yuv_out) {   // warp-uniform
+        const int cw = (W + 1) >> 1, chh = (H + 1) >> 1;
+        unsigned char* const Yp = A.yuv_out;
+        unsigned char* const Up = Yp + (size_t)W * H;
+        unsigned char* const Vp = Up + (size_t)cw * chh;
+        FOR4 {
+            const int x = S.xs[SX(p)], y = S.ys[SY(p)];
+            const int r = ncr_to_u8(dr[p]), g = ncr_to_u8(dg[p]), b = ncr_to_u8(db[p]);
+            if (valid[p]) Yp[(size_t)y * W + x] = (unsigned char)(((66 * r + 129 * g + 25 * b + 128) >> 8) + 16);
+            const uint32_t pk = (uint32_t)r | ((uint32_t)g << 10) | ((uint32_t)b << 20);
+            const uint32_t side = __shfl_xor_sync(FULL, pk, 1);
+            const uint32_t row = pk + (((x ^ 1) < W) ? side : pk);
+            const uint32_t other = __shfl_xor_sync(FULL, row, 8);
+            const uint32_t sum = row + (((y ^ 1) < H) ? other : row);
+            if (valid[p] && !((x | y) & 1)) {
+                const int mr = (int)((sum & 1023u) + 2u) >> 2, mg = (int)(((sum >> 10) & 1023u) + 2u) >> 2,
+                          mb = (int)((sum >> 20) + 2u) >> 2;
+                const size_t ci = (size_t)(y >> 1) * cw + (x >> 1);
+                Up[ci] = (unsigned char)(((-38 * mr - 74 * mg + 112 * mb + 128) >> 8) + 128);
+                Vp[ci] = (unsigned char)(((112 * mr - 94 * mg - 18 * mb + 128) >> 8) + 128);
+            }
+        }
+    }
+    return staged_next;
+}
+
+// Claims the next region (dynamic scheduling: one global counter).  `atom.inc` is used instead of atomicAdd so that ptxas does
+// not turn the claim into its warp-aggregated form, whose result shuffle would make the warp wait for the atomic right here.
+__device__ __forceinline__ uint32_t claim_region(uint32_t* counter) {
+    uint32_t t;
+    asm volatile("atom.global.inc.u32 %0, [%1], 0xffffffff;" : "=r"(t) : "l"(counter) : "memory");
+    return t;
+}
+
+// PREFETCH = false: claim a region, read its header and list, composite it (the in-region command prefetch is the only
+// look-ahead) — the variant for long lists, where the per-region latency chain is amortised over many commands.
+// PREFETCH = true: the variant for short lists (chart / video frames: a handful of commands per region), where that chain
+// (claim -> header -> list -> first command, four dependent round trips to L2) is most of a region's time.  The chain of
+// region t+1 runs while region t is composited: the claim for t+2 is issued at the start of t and consumed at its end; the
+// header of t+1 is loaded at the end of t-1, its list entries at the start of t, its first command during t's last command.
+template <bool ALPHA, bool COUNT, bool PREFETCH>
 __global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, NCR_COMPOSITE_MIN_CTAS) ncr_composite(NcrFlushArgs A) {
     // u8 / 255.0 (CreateTextureUInt8, cpp:350), IEEE division on both sides.  32 copies, copy c of entry k at [k*32 + c]:
     // a lane only ever reads its own copy, so lookups never collide on a bank.
     double* s_lut = (double*)ncr_smem;
     // Per-warp double-buffered command slot: the next command of the list is fetched while the current one is applied.
-    NcrCmd (*s_cmd)[2] = (NcrCmd (*)[2])(ncr_smem + NCR_LUT_BYTES);
+    NcrCmd (*s_cmd_all)[2] = (NcrCmd (*)[2])(ncr_smem + NCR_LUT_BYTES);
     // One division per entry (256 per CTA, not 256 x copies: the init is ~10 % of a low-overdraw launch otherwise), then
     // each value is replicated by its thread.
     for (int k = threadIdx.x; k < 256; k += NCR_COMPOSITE_THREADS) {
@@ -553,140 +737,48 @@ __global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, NCR_COMPOSITE_MIN_CTAS)
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double* lut = s_lut;
-    const uint32_t lut_base = (uint32_t)lane * 8u;
-    const int lx = lane & 7, ly = lane >> 3;
-    const int n_tiles = A.d.tiles_x * A.d.tiles_y;
-    const int n_tasks = n_tiles * NCR_TASKS_PER_TILE;
-    constexpr int IPP = ALPHA ? 4 : 3;
-    constexpr uint32_t WORDS = NCR_CMD_WORDS16;   // 15 x 16 B
-    const int W = A.d.w, H = A.d.h;
+    NcrCmd (*s_cmd)[2] = s_cmd_all + warp;
+    const int n_tasks = A.d.tiles_x * A.d.tiles_y * NCR_TASKS_PER_TILE;
+    const uint2* __restrict__ hdr = (const uint2*)A.fine_off;   // per region: {offset, count}
     unsigned long long n_applied = 0;
+    int slot = 0;
 
-    for (;;) {
-        int task = 0;
-        if (lane == 0) task = (int)atomicAdd(&A.cursors[5], 1u);
-        task = __shfl_sync(FULL, task, 0);
-        if (task >= n_tasks) break;
-        const int tile = task / NCR_TASKS_PER_TILE, sub = task % NCR_TASKS_PER_TILE;
-        const uint32_t loff = __ldg(&A.fine_off[tile]);
-        const uint32_t lcount = __ldg(&A.fine_off[n_tiles + tile]);
-        if (lcount == 0 && A.u8_out == nullptr && A.yuv_out == nullptr) continue;
-
-        const int x0 = (tile % A.d.tiles_x) * NCR_TILE + (sub % (16 / NCR_RW)) * NCR_RW;
-        const int y0 = (tile / A.d.tiles_x) * NCR_TILE + (sub / (16 / NCR_RW)) * NCR_RH;
-        if (y0 >= H || x0 >= W) continue;
-        Slots S;
-#pragma unroll
-        for (int k = 0; k < NCR_NX; ++k) { S.xs[k] = x0 + 8 * k + lx; S.fx[k] = (double)S.xs[k]; }
-#pragma unroll
-        for (int k = 0; k < NCR_NY; ++k) { S.ys[k] = y0 + 4 * k + ly; S.fy[k] = (double)S.ys[k]; }
-        bool valid[NCR_P];
-        FOR4 valid[p] = S.xs[SX(p)] < W && S.ys[SY(p)] < H;
-
-        double dr[NCR_P], dg[NCR_P], db[NCR_P], da[NCR_P];
-        FOR4 { dr[p] = 0.0; dg[p] = 0.0; db[p] = 0.0; da[p] = 0.0; }
-        // The canvas is read unless the list starts with a SetColor (then every pixel is overwritten first).
-        if (A.load_fb != 0 || lcount == 0) {
-            FOR4 if (valid[p]) {
-                const double* q = A.fb + ((size_t)S.ys[SY(p)] * W + S.xs[SX(p)]) * IPP;
-                if (ALPHA) {
-                    const double2 lo = ((const double2*)q)[0], hi = ((const double2*)q)[1];
-                    dr[p] = lo.x; dg[p] = lo.y; db[p] = hi.x; da[p] = hi.y;
-                } else {
-                    dr[p] = q[0]; dg[p] = q[1]; db[p] = q[2];
-                }
-            }
+    if (!PREFETCH) {
+        for (;;) {
+            int task = 0;
+            if (lane == 0) task = (int)atomicAdd(&A.cursors[5], 1u);
+            task = __shfl_sync(FULL, task, 0);
+            if (task >= n_tasks) break;
+            const uint2 h = __ldg(hdr + task);
+            uint32_t ents = 0;
+            if ((uint32_t)lane < h.y) ents = __ldg(A.fine_list + h.x + lane);   // first 32 entries, one coalesced load
+            run_region<ALPHA, COUNT>(A, s_cmd, task, h.x, h.y, ents, slot, false, false, 0u, s_lut, n_applied);
         }
-
-        // Walk the tile's list in submission order.  32 entries at a time: each lane tests one command's box against
-        // this half-tile, the ballot is the set of commands to apply.
-        uint32_t k0 = 0, pending = 0, mine = 0;
-        auto next_cmd = [&]() -> int {   // warp-uniform: index of the next command touching this half, or -1
-            while (pending == 0) {
-                if (k0 >= lcount) return -1;
-                bool hit = false;
-                if (k0 + lane < lcount) {
-                    mine = __ldg(&A.fine_list[loff + k0 + lane]);
-                    const int4 box = __ldg((const int4*)&A.boxes[mine]);   // l, r, t, b
-                    hit = box.z < y0 + NCR_RH && box.w > y0 && box.x < x0 + NCR_RW && box.y > x0;
-                    if (hit) hit = !quad_misses_region(A.cmds + mine, max(x0, box.x), min(x0 + NCR_RW, box.y) - 1,
-                                                       max(y0, box.z), min(y0 + NCR_RH, box.w) - 1);
-                }
-                pending = __ballot_sync(FULL, hit);
-                k0 += 32;
-            }
-            const int kk = __ffs(pending) - 1;
-            pending &= pending - 1;
-            return (int)__shfl_sync(FULL, mine, kk);
-        };
-
-        int slot = 0;
-        int cur = next_cmd();
-        if (cur >= 0) {
-            if (lane < WORDS) ((uint4*)&s_cmd[warp][0])[lane] = __ldg((const uint4*)(A.cmds + cur) + lane);
-            __syncwarp();
-        }
-        while (cur >= 0) {
-            const int nxt = next_cmd();
-            uint4 pre = make_uint4(0, 0, 0, 0);
-            if (nxt >= 0 && lane < WORDS) pre = __ldg((const uint4*)(A.cmds + nxt) + lane);   // in flight during apply_cmd
-            apply_cmd<ALPHA, COUNT>(s_cmd[warp][slot], A, S, lut, lut_base, dr, dg, db, da, n_applied);
-            if (nxt >= 0 && lane < WORDS) ((uint4*)&s_cmd[warp][slot ^ 1])[lane] = pre;
-            __syncwarp();
-            slot ^= 1;
-            cur = nxt;
-        }
-
-        // tile write-back: canonical f64 canvas (only if something was drawn) and the fused (iu8)(v*255) image
-        FOR4 if (valid[p]) {
-            const size_t pix = ((size_t)S.ys[SY(p)] * W + S.xs[SX(p)]) * IPP;
-            if (lcount != 0) {
-                double* q = A.fb + pix;
-                if (ALPHA) {
-                    ((double2*)q)[0] = make_double2(dr[p], dg[p]);
-                    ((double2*)q)[1] = make_double2(db[p], da[p]);
-                } else {
-                    q[0] = dr[p]; q[1] = dg[p]; q[2] = db[p];
-                }
-            }
-            if (A.u8_out) {
-                if (ALPHA) {
-                    const uint32_t o = (uint32_t)ncr_to_u8(dr[p]) | ((uint32_t)ncr_to_u8(dg[p]) << 8) |
-                                       ((uint32_t)ncr_to_u8(db[p]) << 16) | ((uint32_t)ncr_to_u8(da[p]) << 24);
-                    ((uint32_t*)A.u8_out)[(size_t)S.ys[SY(p)] * W + S.xs[SX(p)]] = o;
-                } else {
-                    unsigned char* o = A.u8_out + pix;
-                    o[0] = ncr_to_u8(dr[p]); o[1] = ncr_to_u8(dg[p]); o[2] = ncr_to_u8(db[p]);
-                }
-            }
-        }
-        // Present path, fused: the YUV 4:2:0 planes of the (iu8)(v*255) image, same arithmetic as ncr_yuv420p
-        // (kernels.cu).  A 2x2 chroma block is (lane, lane^1) x (lane, lane^8) of the same pixel slot — region origins are
-        // even — so the block sums are two shuffles of the packed 10-bit channel sums; a missing neighbour column / row
-        // (odd canvas size) is replaced by the pixel's own, which is the edge replication of the standalone kernel.
-        if (A.yuv_out) {   // warp-uniform
-            const int cw = (W + 1) >> 1, chh = (H + 1) >> 1;
-            unsigned char* const Yp = A.yuv_out;
-            unsigned char* const Up = Yp + (size_t)W * H;
-            unsigned char* const Vp = Up + (size_t)cw * chh;
-            FOR4 {
-                const int x = S.xs[SX(p)], y = S.ys[SY(p)];
-                const int r = ncr_to_u8(dr[p]), g = ncr_to_u8(dg[p]), b = ncr_to_u8(db[p]);
-                if (valid[p]) Yp[(size_t)y * W + x] = (unsigned char)(((66 * r + 129 * g + 25 * b + 128) >> 8) + 16);
-                const uint32_t pk = (uint32_t)r | ((uint32_t)g << 10) | ((uint32_t)b << 20);
-                const uint32_t side = __shfl_xor_sync(FULL, pk, 1);
-                const uint32_t row = pk + (((x ^ 1) < W) ? side : pk);
-                const uint32_t other = __shfl_xor_sync(FULL, row, 8);
-                const uint32_t sum = row + (((y ^ 1) < H) ? other : row);
-                if (valid[p] && !((x | y) & 1)) {
-                    const int mr = (int)((sum & 1023u) + 2u) >> 2, mg = (int)(((sum >> 10) & 1023u) + 2u) >> 2,
-                              mb = (int)((sum >> 20) + 2u) >> 2;
-                    const size_t ci = (size_t)(y >> 1) * cw + (x >> 1);
-                    Up[ci] = (unsigned char)(((-38 * mr - 74 * mg + 112 * mb + 128) >> 8) + 128);
-                    Vp[ci] = (unsigned char)(((112 * mr - 94 * mg - 18 * mb + 128) >> 8) + 128);
-                }
-            }
+    } else {
+        uint32_t t_cur = 0, t_nxt = 0;
+        if (lane == 0) { t_cur = claim_region(&A.cursors[5]); t_nxt = claim_region(&A.cursors[5]); }
+        t_cur = __shfl_sync(FULL, t_cur, 0);
+        t_nxt = __shfl_sync(FULL, t_nxt, 0);
+        uint2 h_cur = make_uint2(0, 0), h_nxt = make_uint2(0, 0);
+        if (t_cur < (uint32_t)n_tasks) h_cur = __ldg(hdr + t_cur);
+        if (t_nxt < (uint32_t)n_tasks) h_nxt = __ldg(hdr + t_nxt);
+        uint32_t e_cur = 0;
+        if ((uint32_t)lane < h_cur.y) e_cur = __ldg(A.fine_list + h_cur.x + lane);
+        bool have0 = false;
+        while (t_cur < (uint32_t)n_tasks) {
+            uint32_t t_aft = 0;
+            if (lane == 0) t_aft = claim_region(&A.cursors[5]);   // region t+2: in flight for the whole of region t
+            uint32_t e_nxt = 0;
+            if ((uint32_t)lane < h_nxt.y) e_nxt = __ldg(A.fine_list + h_nxt.x + lane);   // h_nxt is {0,0} past the end
+            const bool next_valid = h_nxt.y != 0;
+            const uint32_t next_e0 = __shfl_sync(FULL, e_nxt, 0);
+            have0 = run_region<ALPHA, COUNT>(A, s_cmd, (int)t_cur, h_cur.x, h_cur.y, e_cur, slot, have0, next_valid, next_e0,
+                                             s_lut, n_applied);
+            t_cur = t_nxt; h_cur = h_nxt; e_cur = e_nxt;
+            asm volatile("" : "+r"(t_aft) :: "memory");   // the claim's result is first needed here, after the region's stores
+            t_nxt = __shfl_sync(FULL, t_aft, 0);
+            h_nxt = make_uint2(0, 0);
+            if (t_nxt < (uint32_t)n_tasks) h_nxt = __ldg(hdr + t_nxt);
         }
     }
 
@@ -696,35 +788,38 @@ __global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, NCR_COMPOSITE_MIN_CTAS)
     }
 }
 
-int g_grid[4] = {0, 0, 0, 0};
+// One grid size per (device, kernel variant): every resident CTA slot, one wave.
+int g_grid[64][8];
 
-template <bool ALPHA, bool COUNT>
-void launch(const NcrFlushArgs& A, cudaStream_t s, int slot) {
-    if (g_grid[slot] == 0) {
-        int dev = 0, sms = 148, per_sm = 1;
-        cudaGetDevice(&dev);
+template <bool ALPHA, bool COUNT, bool PREFETCH>
+void launch(const NcrFlushArgs& A, cudaStream_t s, int variant) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (g_grid[dev][variant] == 0) {
+        int sms = 148, per_sm = 1;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(ncr_composite<ALPHA, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, NCR_SMEM_BYTES);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ncr_composite<ALPHA, COUNT>, NCR_COMPOSITE_THREADS, NCR_SMEM_BYTES);
-        g_grid[slot] = sms * (per_sm > 0 ? per_sm : 1);   // persistent: every resident CTA slot, one wave
+        cudaFuncSetAttribute(ncr_composite<ALPHA, COUNT, PREFETCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, NCR_SMEM_BYTES);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ncr_composite<ALPHA, COUNT, PREFETCH>, NCR_COMPOSITE_THREADS, NCR_SMEM_BYTES);
+        g_grid[dev][variant] = sms * (per_sm > 0 ? per_sm : 1);   // persistent: every resident CTA slot, one wave
     }
     const int n_tasks = A.d.tiles_x * A.d.tiles_y * NCR_TASKS_PER_TILE;
     const int warps = NCR_COMPOSITE_THREADS / 32;
-    int grid = g_grid[slot];
+    int grid = g_grid[dev][variant];
     if (grid * warps > n_tasks) grid = (n_tasks + warps - 1) / warps;
     if (grid < 1) grid = 1;
-    ncr_composite<ALPHA, COUNT><<<grid, NCR_COMPOSITE_THREADS, NCR_SMEM_BYTES, s>>>(A);
+    ncr_composite<ALPHA, COUNT, PREFETCH><<<grid, NCR_COMPOSITE_THREADS, NCR_SMEM_BYTES, s>>>(A);
 }
 
 }   // namespace
 
 extern "C" void ncr_launch_composite(const NcrFlushArgs* A, cudaStream_t s) {
-    const bool alpha = A->d.ipp == 4, count = A->count_pixels != 0;
+    const bool alpha = A->d.ipp == 4, count = A->count_pixels != 0, pre = A->prefetch != 0;
     if (alpha) {
-        if (count) launch<true, true>(*A, s, 0);
-        else launch<true, false>(*A, s, 1);
+        if (count) { if (pre) launch<true, true, true>(*A, s, 0); else launch<true, true, false>(*A, s, 1); }
+        else       { if (pre) launch<true, false, true>(*A, s, 2); else launch<true, false, false>(*A, s, 3); }
     } else {
-        if (count) launch<false, true>(*A, s, 2);
-        else launch<false, false>(*A, s, 3);
+        if (count) { if (pre) launch<false, true, true>(*A, s, 4); else launch<false, true, false>(*A, s, 5); }
+        else       { if (pre) launch<false, false, true>(*A, s, 6); else launch<false, false, false>(*A, s, 7); }
     }
 }

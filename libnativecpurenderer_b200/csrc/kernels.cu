@@ -14,6 +14,7 @@
 #include "kernels.h"
 
 #include "pixel_math.cuh"
+#include "region_test.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // binning
@@ -123,11 +124,19 @@ __global__ void __launch_bounds__(32 * NCR_COARSE_WARPS) ncr_bin_coarse(NcrFlush
     }
 }
 
-// One warp per 16x16-px tile: the tile's bin list is filtered by the tile's pixel rectangle, 128 candidates per step
-// (four independent index -> box load chains per lane), and compacted in order with ballot + popc.
+// One warp per 16x16-px tile.  The tile's bin list is filtered by the tile's pixel rectangle (four independent index -> box
+// load chains per lane per step), the survivors are classified EXACTLY against the tile's two 16x8 regions
+// (ncr_region_codes: rejected / may touch / interior), and each region's survivors are compacted in submission order with
+// ballot + popc.  So the composite's list walk performs no test and no gather: every entry it reads is a command to run.
+//
+// One pass: hits are staged in shared memory (NCR_FINE_STAGE entries per region per warp) while they are counted, then one
+// atomicAdd carves the tile's two runs out of the list array and the staged entries are copied out coalesced.  A region with
+// more hits than the stage holds re-scans and writes directly (second pass).
+#define NCR_FINE_STAGE 320
 __global__ void __launch_bounds__(256) ncr_bin_fine(NcrFlushArgs A) {
-    const int lane = threadIdx.x & 31;
-    const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);
+    __shared__ uint32_t s_stage[8][2][NCR_FINE_STAGE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = blockIdx.x * 8 + warp;
     const int n_tiles = A.d.tiles_x * A.d.tiles_y;
     if (tile >= n_tiles) return;
     const int tx = tile % A.d.tiles_x, ty = tile / A.d.tiles_x;
@@ -135,83 +144,67 @@ __global__ void __launch_bounds__(256) ncr_bin_fine(NcrFlushArgs A) {
     const int bin = (ty / NCR_COARSE) * A.d.bins_x + tx / NCR_COARSE;
     const uint32_t cbase = A.coarse_off[bin];
     const uint32_t ccount = A.coarse_off[A.d.bins_x * A.d.bins_y + bin];
+    const int r0 = tile * NCR_REGIONS_PER_TILE;
 
-    uint32_t count = 0;
     if (ccount == 0) {
-        if (lane == 0) { A.fine_off[tile] = 0; A.fine_off[n_tiles + tile] = 0; }
+        if (lane < 2) ((uint2*)A.fine_off)[r0 + lane] = make_uint2(0u, 0u);
         return;
     }
-    if (ccount <= 128) {
-        // Short bin list (the common case of chart-like frames): one step holds every candidate in registers, so the list is
-        // read once — count, allocate, write, without the second scan.
-        uint32_t idx[4], m[4];
-        bool hit[4];
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t cnt[2] = {0, 0};
+    uint32_t off[2] = {0, 0};
+    for (int pass = 0; pass < 2; ++pass) {
+        uint32_t pos[2] = {0, 0};
+        for (uint32_t k = 0; k < ccount; k += 32 * NCR_FINE_U) {
+            uint32_t idx[NCR_FINE_U], code[NCR_FINE_U];
+            int4 bxs[NCR_FINE_U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) idx[u] = A.coarse_list[cbase + min(u * 32 + lane, ccount - 1)];   // clamped, unconditional
+            for (int u = 0; u < NCR_FINE_U; ++u) idx[u] = A.coarse_list[cbase + min(k + u * 32 + lane, ccount - 1)];   // clamped, unconditional
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const NcrBox b = A.boxes[idx[u]];
-            hit[u] = box_hits(b, x0, y0, x1, y1) && (u * 32 + lane < ccount);
+            for (int u = 0; u < NCR_FINE_U; ++u) bxs[u] = __ldg((const int4*)&A.boxes[idx[u]]);
+#pragma unroll
+            for (int u = 0; u < NCR_FINE_U; ++u) {
+                const bool in_tile = bxs[u].x < bxs[u].y && bxs[u].z < bxs[u].w && bxs[u].x < x1 && bxs[u].y > x0 && bxs[u].z < y1 &&
+                                     bxs[u].w > y0 && (k + u * 32 + lane < ccount);
+                code[u] = in_tile ? ncr_region_codes(A.cmds + idx[u], bxs[u], x0, y0) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < NCR_FINE_U; ++u) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t cd = (code[u] >> (2 * h)) & 3u;
+                    const uint32_t m = __ballot_sync(0xffffffffu, cd != 0u);
+                    if (cd) {
+                        const uint32_t at = pos[h] + __popc(m & lt);
+                        const uint32_t e = idx[u] | (cd == 2u ? NCR_ENTRY_INTERIOR : 0u);
+                        if (pass == 0) { if (at < NCR_FINE_STAGE) s_stage[warp][h][at] = e; }
+                        else A.fine_list[off[h] + at] = e;
+                    }
+                    pos[h] += __popc(m);
+                }
+            }
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { m[u] = __ballot_sync(0xffffffffu, hit[u]); count += __popc(m[u]); }
-        uint32_t off = 0;
+        if (pass == 1) return;
+        cnt[0] = pos[0]; cnt[1] = pos[1];
+        uint32_t base = 0, total = cnt[0] + cnt[1];
         if (lane == 0) {
-            off = count ? atomicAdd(&A.cursors[1], count) : 0u;
-            if (off + count > A.fine_cap) { count = 0; atomicExch(&A.cursors[4], 2u); }
-            A.fine_off[tile] = off;
-            A.fine_off[n_tiles + tile] = count;
+            base = total ? atomicAdd(&A.cursors[1], total) : 0u;
+            if (base + total > A.fine_cap) { total = 0; atomicExch(&A.cursors[4], 2u); }
         }
-        off = __shfl_sync(0xffffffffu, off, 0);
-        count = __shfl_sync(0xffffffffu, count, 0);
-        if (count == 0) return;
+        base = __shfl_sync(0xffffffffu, base, 0);
+        total = __shfl_sync(0xffffffffu, total, 0);
+        if (total == 0) cnt[0] = cnt[1] = 0;
+        off[0] = base; off[1] = base + cnt[0];
+        if (lane < 2) ((uint2*)A.fine_off)[r0 + lane] = make_uint2(off[lane], cnt[lane]);
+        if (total == 0) return;
+        if (cnt[0] <= NCR_FINE_STAGE && cnt[1] <= NCR_FINE_STAGE) {
+            __syncwarp();
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (hit[u]) A.fine_list[off + __popc(m[u] & ((1u << lane) - 1))] = idx[u];
-            off += __popc(m[u]);
+            for (int h = 0; h < 2; ++h)
+                for (uint32_t i = lane; i < cnt[h]; i += 32) A.fine_list[off[h] + i] = s_stage[warp][h][i];
+            return;
         }
-        return;
-    }
-    // longer lists: NCR_FINE_U independent index -> box chains per lane per step (the scan is round-trip bound)
-    for (uint32_t k = 0; k < ccount; k += 32 * NCR_FINE_U) {
-        uint32_t idx[NCR_FINE_U];
-        bool hit[NCR_FINE_U];
-#pragma unroll
-        for (int u = 0; u < NCR_FINE_U; ++u) idx[u] = A.coarse_list[cbase + min(k + u * 32 + lane, ccount - 1)];   // clamped, unconditional
-#pragma unroll
-        for (int u = 0; u < NCR_FINE_U; ++u) {
-            const NcrBox b = A.boxes[idx[u]];
-            hit[u] = box_hits(b, x0, y0, x1, y1) && (k + u * 32 + lane < ccount);
-        }
-#pragma unroll
-        for (int u = 0; u < NCR_FINE_U; ++u) count += __popc(__ballot_sync(0xffffffffu, hit[u]));
-    }
-    uint32_t off = 0;
-    if (lane == 0) {
-        off = atomicAdd(&A.cursors[1], count);
-        if (off + count > A.fine_cap) { count = 0; atomicExch(&A.cursors[4], 2u); }
-        A.fine_off[tile] = off;
-        A.fine_off[n_tiles + tile] = count;
-    }
-    off = __shfl_sync(0xffffffffu, off, 0);
-    count = __shfl_sync(0xffffffffu, count, 0);
-    if (count == 0) return;
-    for (uint32_t k = 0; k < ccount; k += 32 * NCR_FINE_U) {
-        uint32_t idx[NCR_FINE_U];
-        bool hit[NCR_FINE_U];
-#pragma unroll
-        for (int u = 0; u < NCR_FINE_U; ++u) idx[u] = A.coarse_list[cbase + min(k + u * 32 + lane, ccount - 1)];   // clamped, unconditional
-#pragma unroll
-        for (int u = 0; u < NCR_FINE_U; ++u) {
-            const NcrBox b = A.boxes[idx[u]];
-            hit[u] = box_hits(b, x0, y0, x1, y1) && (k + u * 32 + lane < ccount);
-        }
-#pragma unroll
-        for (int u = 0; u < NCR_FINE_U; ++u) {
-            const uint32_t m = __ballot_sync(0xffffffffu, hit[u]);
-            if (hit[u]) A.fine_list[off + __popc(m & ((1u << lane) - 1))] = idx[u];
-            off += __popc(m);
-        }
+        // a region's list outgrew the stage: second pass writes straight to the list array
     }
 }
 

@@ -62,8 +62,16 @@ struct alignas(16) NcrBox {
     int32_t l, r, t, b;
 };
 
-#define NCR_TILE 16            // composite tile edge in pixels
+#define NCR_TILE 16            // binning tile edge in pixels
 #define NCR_COARSE 8           // coarse bin edge in tiles (128 px)
+// The composite's work unit is a REGION: the top or bottom 16x8-px half of a tile (region = 2 * tile + half).  ncr_bin_fine
+// writes one ordered command list per region.  A list entry is a command index; bit 31 marks the command as INTERIOR to
+// the region: every pixel of the region provably passes the command's box and coverage tests (see region_code()).
+#define NCR_REGION_W 16
+#define NCR_REGION_H 8
+#define NCR_REGIONS_PER_TILE 2
+#define NCR_ENTRY_INTERIOR 0x80000000u
+#define NCR_ENTRY_INDEX 0x7fffffffu
 
 struct NcrFrameDims {
     int32_t w, h, ipp;
@@ -85,10 +93,13 @@ struct NcrFlushArgs {
     uint32_t load_fb;           // 0: every tile's list starts with SET_COLOR, do not read fb
     uint32_t* coarse_list;      // capacity coarse_cap
     uint32_t* coarse_off;       // [bins] offset, [bins] count
-    uint32_t* fine_list;        // capacity fine_cap
-    uint32_t* fine_off;         // [tiles] offset, [tiles] count
+    uint32_t* fine_list;        // capacity fine_cap; entries: command index | NCR_ENTRY_INTERIOR
+    uint32_t* fine_off;         // per region: {offset, count} (uint2[regions])
     uint32_t* cursors;          // [0] coarse cursor, [1] fine cursor, [2..3] blended-pixel counter (u64), [4] overflow flag,
-                                // [5] composite work counter (half-tiles handed out)
+                                // [5] composite work counter (regions handed out)
     uint32_t coarse_cap, fine_cap;
     uint32_t count_pixels;      // stats mode: count APPLY executions
+    uint32_t write_fb;          // 0: present-only flush — the f64 canvas is NOT written back (the host marks it stale and
+                                // re-runs this batch with write_fb = 1 if anyone ever reads it; see api.cu materialize())
+    uint32_t prefetch;          // composite variant: 1 = next region's header / list / first command fetched during the current one
 };

@@ -643,3 +643,92 @@ def test_frame_pool_reports_bad_frames(gpu, image_rgba):
             pool.render(bad, tex)
         seen = []
         assert pool.render(good, tex, on_frame=lambda i, px: seen.append(i)) == 9 and seen == list(range(9))
+
+
+def test_present_only_flush_leaves_a_recoverable_canvas(gpu, port, image_rgba):
+    """GetBufferAsUInt8 / YUV flushes do not write the f64 canvas back (present-only flush); every later
+    consumer of the canvas — more draws without SetColor, GetBuffer, GetColor, canvas -> texture, a shared alias — must
+    still see exactly what the reference's immediate-mode canvas holds."""
+    outs = []
+    for R in (gpu, port):
+        out = []
+        tex = cases.tiny_textures(R, image_rgba)
+        ctx = R.RenderContext(150, 90, True)
+        ctx.set_color(.1, .2, .3, 1)
+        streams.stream_random(ctx, tex, 501, n=40)
+        out.append(cases.sha(ctx.get_buffer_as_uint8()))           # present-only flush
+        streams.stream_random(ctx, tex, 502, n=40)                 # draws on top of the (stale) canvas, no SetColor
+        out.append(cases.sha(ctx.get_buffer_as_uint8()))
+        out.append(cases.sha(ctx.get_buffer_np().tobytes()))        # f64 canvas after two presents
+        ctx.draw_circle(40, 40, 25, 1, 0, 1, .5)
+        out.append(cases.sha(ctx.get_buffer_as_uint8()))
+        out.append(ctx.get_color(41.5, 39.0))                       # single-pixel read of a presented canvas
+        ctx.fill_color(0, 1, 0, .25)
+        out.append(cases.sha(ctx.get_buffer_as_uint8()))
+        snap = ctx.as_texture()                                     # CreateTextureFromRenderContext after a present
+        shared = ctx.as_texture_shared()
+        dst = R.RenderContext(64, 64, True)
+        dst.set_color(0, 0, 0, 1)
+        dst.translate(2, 3)
+        dst.rotate(.3)
+        dst.draw_texture(snap, 0, 0, 50, 40)
+        dst.draw_texture(shared, 10, 10, 40, 50)
+        out.append(cases.digest(dst))
+        ctx.set_color(.5, .5, .5, .5)                               # a stale canvas that is overwritten, never read
+        ctx.draw_rect(5, 5, 60, 30, 1, 0, 0, .5)
+        out.append(cases.sha(ctx.get_buffer_as_uint8()))
+        out.append(cases.sha(ctx.get_buffer_as_uint8()))            # nothing pending: cached image
+        out.append(cases.sha(ctx.get_buffer_np().tobytes()))
+        outs.append(out)
+    assert outs[0] == outs[1]
+
+
+def test_video_frames_never_write_the_canvas_back(gpu, image_rgba):
+    """A milrenderer-shaped loop (SetColor ... GetBufferAsUInt8 per frame, mil:866-1036) runs one composite per frame and
+    never has to bring a canvas up to date."""
+    ctx = gpu.RenderContext(320, 180, False)
+    tex = cases.tiny_textures(gpu, image_rgba)
+    before = ctx.stats()
+    for f in range(6):
+        ctx.set_color(0, 0, 0, 0)
+        streams.stream_random(ctx, tex, 600 + f, n=30)
+        ctx.get_buffer_as_uint8()
+    st = ctx.stats()
+    assert st.materialized == before.materialized == 0
+    assert st.flushes - before.flushes == 6
+    assert st.kernel_launches - before.kernel_launches == 18   # bin_coarse + bin_fine + composite per frame
+
+
+def test_u8_truncation_edge_values_on_the_gpu(gpu, port):
+    """(iu8)(v*255) of out-of-range canvas values (cpp:52-57: cvttsd2si semantics — truncation toward zero, low byte of a
+    32-bit conversion, NaN / overflow -> 0x80000000 -> 0): through the composite's fused u8 image, through the standalone
+    convert kernel, through the fused and standalone YUV paths, and blended on top of (NaN and inf propagate through
+    dst*(1-a)+src*a exactly as in IEEE f64).  Expected bytes are the reference's own (tests/test_oracle.py checks the same
+    list against the unmodified reference build)."""
+    vals = [2.0, -0.01, 1e10, 300.7 / 255, float("nan"), -1e10, 1.0, 0.999999, 0.625, 1 / 3]
+    outs = []
+    for R in (gpu, port):
+        out = []
+        for alpha in (True, False):
+            ctx = R.RenderContext(20, 10, alpha)
+            ctx.set_color(0, 0, 0, 0)
+            ctx.set_pixel(0, 0, *vals[0:4])
+            ctx.set_pixel(1, 0, *vals[4:8])
+            ctx.set_pixel(2, 0, vals[8], vals[9], 0, 0)
+            ctx.set_pixel(17, 9, float("inf"), -float("inf"), -0.0, 1e300)
+            fused = bytes(ctx.get_buffer_as_uint8())
+            out.append(list(fused[:12]))
+            out.append(cases.sha(fused))
+            out.append(cases.sha(ctx.get_buffer_as_yuv420p().tobytes()))
+            if R is gpu: ctx.flush()                        # (the CPU checker is immediate-mode: nothing to flush)
+            ctx.draw_rect(19, 9, 1, 1, 0, 0, 0, 0)        # invalidates the cached images without changing those pixels
+            if R is gpu: ctx.flush()
+            out.append(cases.sha(ctx.get_buffer_as_uint8()))                       # standalone convert kernel
+            out.append(cases.sha(ctx.get_buffer_as_yuv420p().tobytes()))          # standalone YUV kernel
+            ctx.fill_color(.25, .5, .75, .5)                                       # blend over NaN / inf / huge values
+            ctx.draw_rect(0, 0, 3, 1, 1, 1, 1, 1)                                  # a == 1: plain store over them
+            ctx.draw_rect(16, 8, 4, 2, .5, .5, .5, .999)
+            out.append(cases.digest(ctx))
+        outs.append(out)
+    assert outs[0][0] == [254, 254, 0, 44, 0, 0, 255, 254, 159, 85, 0, 0]
+    assert outs[0] == outs[1]
