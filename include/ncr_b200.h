@@ -110,7 +110,7 @@ void ApplySpeedAudioClip(AudioClip* clip, double speed);                  /* h:1
 typedef struct NcrStats {
     unsigned long long n_cmds;          /* commands in the last flush */
     unsigned long long coarse_entries;  /* bin-list entries written by ncr_bin_coarse */
-    unsigned long long fine_entries;    /* tile-list entries written by ncr_bin_fine */
+    unsigned long long fine_entries;    /* region-list entries written by ncr_bin_fine: (command, 16x8 region) pairs that survive the exact test */
     unsigned long long blended_pixels;  /* ApplyPixel executions in the last flush (stats mode & 1) */
     unsigned long long h2d_bytes;       /* cumulative, this context */
     unsigned long long d2h_bytes;       /* cumulative, this context */
@@ -118,6 +118,7 @@ typedef struct NcrStats {
     unsigned long long kernel_launches; /* cumulative, this context */
     float ms_bin_coarse, ms_bin_fine, ms_composite, ms_total; /* last flush, CUDA events (stats mode & 2) */
     unsigned long long materialized;    /* cumulative: batches re-run to bring a stale f64 canvas up to date (see NcrRerunLastFlushEx) */
+    unsigned long long interior_entries; /* of fine_entries: (command, region) pairs proven to cover their whole region (straight-line path) */
 } NcrStats;
 
 /* Devices.  CreateRenderContext / CreateTexture* (section 1) use the process default device: NCR_DEVICE, else LOCAL_RANK,
@@ -151,6 +152,8 @@ int NcrRerunLastFlushEx(RenderContext* ctx, int iters, int flush_l2, float* ms_o
 void NcrGetStats(RenderContext* ctx, NcrStats* out);
 void NcrSetStatsMode(RenderContext* ctx, int mode); /* bit 0: count blended pixels, bit 1: per-kernel events */
 unsigned long long NcrKernelLaunchCount(void);      /* kernels launched by this library since load (all contexts) */
+double NcrMeasureD2HRate(unsigned long long bytes_per_copy, int streams, int iters); /* bytes/s of concurrent device -> pinned-host copies (readback ceiling aid) */
+double NcrMeasureD2HRate(unsigned long long bytes_per_copy, int streams, int iters); /* bytes/s of concurrent device -> pinned-host copies on the default device (readback ceiling aid) */
 double NcrMeasureF64Rate(void);                     /* measured rate of non-fused f64 mul/add instructions per second (roofline aid) */
 
 /* Extensions without a reference implementation (parity unpinned). */

@@ -22,6 +22,7 @@ def _declare(lib) -> None:
         return
     P, L, I = ctypes.c_void_p, ctypes.c_long, ctypes.c_int
     lib.NcrCreateFramePool.restype, lib.NcrCreateFramePool.argtypes = P, (L, L, I, I)
+    lib.NcrCreateFramePoolOnDevices.restype, lib.NcrCreateFramePoolOnDevices.argtypes = P, (L, L, I, I, P, I)
     lib.NcrDestroyFramePool.restype, lib.NcrDestroyFramePool.argtypes = None, (P,)
     lib.NcrFramePoolWorkers.restype, lib.NcrFramePoolWorkers.argtypes = I, (P,)
     lib.NcrFramePoolRender.restype, lib.NcrFramePoolRender.argtypes = L, (P, P, P, L, P, L, I, _SINK, P)
@@ -56,12 +57,20 @@ def _call(renderer, traces: Sequence[np.ndarray], textures, on_frame, invoke) ->
 
 
 class FramePool:
-    """``workers`` render contexts (one CUDA stream each) with their device and pinned buffers, kept between renders."""
+    """``workers`` render contexts (one CUDA stream each) with their device and pinned buffers, kept between renders.
 
-    def __init__(self, renderer, width: int, height: int, alpha: bool, workers: int = 8):
+    ``devices`` spreads the workers over several GPUs of the box (worker k on ``devices[k % len(devices)]``): ONE host
+    process — which is what the reference's ``milrenderer.py`` is — then drives all of them, with frames still delivered
+    in order; textures are created once and copied to each device on first use there."""
+
+    def __init__(self, renderer, width: int, height: int, alpha: bool, workers: int = 8, devices: Sequence[int] | None = None):
         _declare(renderer.lib)
         self._r = renderer
-        self._p = renderer.lib.NcrCreateFramePool(width, height, int(alpha), workers)
+        if devices:
+            arr = (ctypes.c_int * len(devices))(*devices)
+            self._p = renderer.lib.NcrCreateFramePoolOnDevices(width, height, int(alpha), workers, arr, len(devices))
+        else:
+            self._p = renderer.lib.NcrCreateFramePool(width, height, int(alpha), workers)
         if not self._p:
             raise RuntimeError(f"NcrCreateFramePool failed: {renderer.last_error()}")
         self.workers = renderer.lib.NcrFramePoolWorkers(self._p)

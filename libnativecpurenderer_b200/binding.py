@@ -85,6 +85,7 @@ _EXT_ABI = {
     "NcrAllocHost": (_P, (c_ulonglong,)),
     "NcrFreeHost": (None, (_P,)),
     "NcrSubmitTrace": (c_long, (_P, _P, c_long, _P, c_long)),
+    "NcrMeasureD2HRate": (c_double, (c_ulonglong, c_int, c_int)),
     "NcrDeviceCount": (c_int, ()),
     "NcrCreateRenderContextOnDevice": (_P, (c_long, c_long, c_bool, c_int)),
     "NcrContextDevice": (c_int, (_P,)),
@@ -123,6 +124,7 @@ class NcrStats(ctypes.Structure):
         ("ms_composite", c_float),
         ("ms_total", c_float),
         ("materialized", c_ulonglong),
+        ("interior_entries", c_ulonglong),
     ]
 
 
@@ -182,6 +184,21 @@ class Renderer:
             return ""
         msg = self.lib.NcrLastError()
         return msg.decode() if msg else ""
+
+    def context_from_ptr(self, ptr: int, width: int, height: int, enable_alpha: bool) -> "RenderContext":
+        """Wraps a context created through an additive entry point (e.g. ``NcrCreateRenderContextOnDevice``); owned by the wrapper."""
+        ctx = self.RenderContext.__new__(self.RenderContext)
+        ctx.width, ctx.height, ctx.enable_alpha = width, height, enable_alpha
+        ctx._lib = self.lib
+        ctx._ptr = ptr
+        ctx._can_release = True
+        return ctx
+
+    def context_on_device(self, width: int, height: int, enable_alpha: bool, device: int) -> "RenderContext":
+        ptr = self.lib.NcrCreateRenderContextOnDevice(width, height, enable_alpha, device)
+        if not ptr:
+            raise RuntimeError(f"NcrCreateRenderContextOnDevice failed: {self.last_error()}")
+        return self.context_from_ptr(ptr, width, height, enable_alpha)
 
     def texture_from_ptr(self, ptr: int) -> "Texture":
         tex = self.Texture.__new__(self.Texture)

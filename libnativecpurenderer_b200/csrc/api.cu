@@ -8,6 +8,7 @@
 //
 // There is no CPU rendering path in this library: without a usable CUDA device CreateRenderContext and the
 // texture constructors print the reason, record it for NcrLastError() and return NULL.
+#include <cuda.h>            // CUtensorMap types only; the driver entry point is resolved at run time (experiment X5)
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -34,6 +35,11 @@
 // device bookkeeping
 // ------------------------------------------------------------------------------------------------
 namespace {
+
+bool env_flag_early(const char* name) {
+    const char* v = getenv(name);
+    return v && *v && atoi(v) != 0;
+}
 
 std::mutex g_mu;
 int g_dev = -1;   // default device of this process: NCR_DEVICE, else LOCAL_RANK, else 0
@@ -204,6 +210,8 @@ struct NcrTexture {
     std::vector<DevRef> replicas;   // [device]: copies of `buf` on other devices, made on first use there (slots never move)
     std::atomic<unsigned long long> replica_mask{0};   // bit d: replicas[d] is published
     std::vector<unsigned char> shadow;   // host copy of u8 texels, fetched on demand (hit-effect masks)
+    DevRef tmap;                    // experiment X5: device copy of the texture's CUtensorMap (home device, RGBA8, w % 4 == 0)
+    bool tmap_tried = false;
     // alias only: snapshot of the source canvas, reused while the source records nothing new (NcrContext::gen)
     DevRef snap;
     unsigned long long snap_gen = 0;
@@ -267,6 +275,10 @@ struct NcrContext {
     NcrStats stats;
     bool failed = false;   // sticky device error
 
+    // experiment X5: the pending batch's TMA-stageable background draw (see NcrFlushArgs::tma_map)
+    const void* tma_map = nullptr;
+    int32_t tma_cmd = -1, tma_x = 0, tma_y = 0, tma_w = 0, tma_h = 0;
+
     // extensions
     bool clip_on = false;
     i64 clip_l = 0, clip_r = 0, clip_t = 0, clip_b = 0;
@@ -323,6 +335,7 @@ void harvest(NcrContext* c) {
         c->stats.coarse_entries = c->h_cursors[0];
         c->stats.fine_entries = c->h_cursors[1];
         c->stats.blended_pixels = (unsigned long long)c->h_cursors[2] | ((unsigned long long)c->h_cursors[3] << 32);
+        c->stats.interior_entries = c->h_cursors[6];
         if (c->h_cursors[4]) {
             set_error("tile-list overflow", c->h_cursors[4] == 1 ? "coarse list" : "fine list");
             c->failed = true;
@@ -421,7 +434,8 @@ int env_int(const char* name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 const int kPrefetchMode = env_int("NCR_PREFETCH", -1);
-const int kPrefetchMaxMean = env_int("NCR_PREFETCH_MAX_MEAN", 12);
+const int kPrefetchMaxMean = env_int("NCR_PREFETCH_MAX_MEAN", 6);
+const size_t kDirectBinMaxCmds = (size_t)env_int("NCR_DIRECT_BIN_MAX_CMDS", 96);   // up to this many commands per flush: no coarse pass
 
 bool materialize(NcrContext* c) {
     if (!c->fb_stale) return true;
@@ -433,8 +447,8 @@ bool materialize(NcrContext* c) {
     M.write_fb = 1;
     M.count_pixels = 0;
     ncr_launch_flush(&M, c->stream, nullptr);
-    g_launches += 3;
-    c->stats.kernel_launches += 3;
+    g_launches += 2u + (M.coarse_list ? 1u : 0u);
+    c->stats.kernel_launches += 2u + (M.coarse_list ? 1u : 0u);
     c->stats.materialized += 1;
     c->last.write_fb = 1;
     c->elide_block = 8;
@@ -490,7 +504,7 @@ bool flush(NcrContext* c, bool want_u8, bool want_yuv = false) {
     bool ok = c->d_cmds.reserve(c->n) && c->d_boxes.reserve(c->n) && c->d_binbox.reserve(c->n) && c->d_aux.reserve(c->n_aux + 2) &&
               c->d_coarse.reserve(c->coarse_need + 1) && c->d_coarse_off.reserve(2 * n_bins) &&
               c->d_fine.reserve(c->fine_need + 1) && c->d_fine_off.reserve(2 * n_regions) && c->d_cursors.reserve(8);
-    if (ok && want_u8) ok = c->d_u8.reserve(n_elems);
+    if (ok && (want_u8 || want_yuv)) ok = c->d_u8.reserve(n_elems);   // the YUV planes are converted from the u8 image
     if (ok && want_yuv) ok = c->d_yuv.reserve(yuv_bytes_of(c));
     if (!ok) { c->failed = true; return false; }
     ok = CK(cudaMemcpyAsync(c->d_cmds.p, S.cmds.p, c->n * sizeof(NcrCmd), cudaMemcpyHostToDevice, c->stream)) &&
@@ -504,7 +518,7 @@ bool flush(NcrContext* c, bool want_u8, bool want_yuv = false) {
     c->stats.h2d_bytes += c->n * (sizeof(NcrCmd) + sizeof(NcrBox) + sizeof(uint32_t)) + c->n_aux * sizeof(double);
 
     A.fb = (double*)c->fb->p;
-    A.u8_out = want_u8 ? c->d_u8.p : nullptr;
+    A.u8_out = (want_u8 || want_yuv) ? c->d_u8.p : nullptr;
     A.yuv_out = want_yuv ? c->d_yuv.p : nullptr;
     A.cmds = c->d_cmds.p;
     A.boxes = c->d_boxes.p;
@@ -513,13 +527,15 @@ bool flush(NcrContext* c, bool want_u8, bool want_yuv = false) {
     A.aux = c->d_aux.p;
     A.n_cmds = (uint32_t)c->n;
     A.load_fb = c->load_fb ? 1u : 0u;
-    A.coarse_list = c->d_coarse.p;
+    A.coarse_list = c->n <= kDirectBinMaxCmds ? nullptr : c->d_coarse.p;
     A.coarse_off = c->d_coarse_off.p;
     A.fine_list = c->d_fine.p;
     A.fine_off = c->d_fine_off.p;
     A.cursors = c->d_cursors.p;
     A.coarse_cap = (uint32_t)c->d_coarse.cap;
     A.fine_cap = (uint32_t)c->d_fine.cap;
+    A.tma_map = c->tma_map; A.tma_cmd = c->tma_cmd; A.tma_x = c->tma_x; A.tma_y = c->tma_y; A.tma_w = c->tma_w; A.tma_h = c->tma_h;
+    c->tma_map = nullptr; c->tma_cmd = -1;
     A.count_pixels = (c->stats_mode & 1) ? 1u : 0u;
     // present-only flush: skip the canvas write-back unless this caller has been reading canvases between presents
     bool elide = (want_u8 || want_yuv) && kElidePresentWriteback;
@@ -532,8 +548,9 @@ bool flush(NcrContext* c, bool want_u8, bool want_yuv = false) {
                                     : (c->fine_need <= (unsigned long long)kPrefetchMaxMean * n_regions ? 1u : 0u);
     const bool timed = (c->stats_mode & 2) != 0;
     ncr_launch_flush(&A, c->stream, timed ? c->ev : nullptr);
-    g_launches += 3;
-    c->stats.kernel_launches += 3;
+    const unsigned n_kernels = 2u + (A.coarse_list ? 1u : 0u) + (A.yuv_out ? 1u : 0u);
+    g_launches += n_kernels;
+    c->stats.kernel_launches += n_kernels;
     c->ev_pending = timed;
     cudaMemcpyAsync(c->h_cursors, c->d_cursors.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
     c->cursors_pending = true;
@@ -549,7 +566,7 @@ bool flush(NcrContext* c, bool want_u8, bool want_yuv = false) {
     c->n_aux = 0;
     c->coarse_need = c->fine_need = 0;
     c->load_fb = true;
-    c->u8_valid = want_u8;
+    c->u8_valid = want_u8 || want_yuv;
     c->yuv_valid = want_yuv;
     c->fb_stale = elide;
     c->cur ^= 1;
@@ -664,6 +681,34 @@ const DevRef* texels_on_device(NcrTexture* tex, int dev) {
     tex->replicas[dev] = copy;
     tex->replica_mask.fetch_or(1ull << dev, std::memory_order_release);
     return &tex->replicas[dev];
+}
+
+// Experiment X5: a CUtensorMap (2-D, 4-byte elements, 16x8 box) over an RGBA8 texture, in device memory, so that a kernel built
+// with NCR_TMA_IDENT can stage a region's texel box with cp.async.bulk.tensor.  Only when NCR_TMA=1.
+const bool kTmaExperiment = env_flag_early("NCR_TMA");
+
+const void* texture_tmap(NcrTexture* tex, int dev) {
+    if (!kTmaExperiment || tex->alias || tex->is_f64 || !tex->alpha || dev != tex->dev || (tex->w & 3) || tex->w < 16 || tex->h < 8) return nullptr;
+    std::lock_guard<std::mutex> lk(tex->mu);
+    if (tex->tmap_tried) return tex->tmap ? tex->tmap->p : nullptr;
+    tex->tmap_tried = true;
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) return nullptr;
+    alignas(64) CUtensorMap map;
+    const cuuint64_t dims[2] = {(cuuint64_t)tex->w, (cuuint64_t)tex->h};
+    const cuuint64_t strides[1] = {(cuuint64_t)tex->w * 4};
+    const cuuint32_t box[2] = {NCR_REGION_W, NCR_REGION_H}, estr[2] = {1, 1};
+    if (((EncodeFn)fn)(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, tex->buf->p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return nullptr;
+    if (!set_device(dev)) return nullptr;
+    DevRef m = dev_alloc(sizeof(map));
+    if (!m || !CK(cudaMemcpy(m->p, &map, sizeof(map), cudaMemcpyHostToDevice))) return nullptr;
+    tex->tmap = m;
+    return m->p;
 }
 
 // Texture operand of a draw on device `dev`.  Aliases of a canvas (cpp:377-384) are resolved to a snapshot of that canvas
@@ -846,6 +891,7 @@ void ResizeRenderContext(RenderContext* ctx, long width, long height) {
     // cpp:39-45: pixels are discarded, state is kept — pending draws can no longer be observed.
     cudaStreamSynchronize(c->stream);
     c->n = 0; c->n_aux = 0; c->coarse_need = c->fine_need = 0; c->load_fb = true;
+    c->tma_map = nullptr; c->tma_cmd = -1;
     c->gen += 1;
     c->refs.clear();
     alloc_canvas(c, width, height);
@@ -1025,6 +1071,7 @@ void SetColor(RenderContext* ctx, double r, double g, double b, double a) {
     // and the composite need not read the canvas back.
     c->n = 0; c->n_aux = 0; c->coarse_need = c->fine_need = 0;
     c->refs.clear();
+    c->tma_map = nullptr; c->tma_cmd = -1;
     NcrCmd* cmd = begin_cmd(c, NCR_OP_SET_COLOR, 0, c->w, 0, c->h, false);
     if (!cmd) return;
     c->load_fb = false;
@@ -1082,6 +1129,14 @@ void DrawTexture(RenderContext* ctx, Texture* tex_, double x, double y, double w
         cmd->x = x; cmd->y = y; cmd->xw = xw; cmd->yh = yh;
         cmd->sx = scaleX; cmd->sy = scaleY;
         cmd->p[0] = (double)i0; cmd->p[1] = (double)j0;
+        if (kTmaExperiment && c->tma_cmd < 0 && scaleX == 1.0 && scaleY == 1.0 && x == (double)i0 && y == (double)j0 &&
+            (cmd->flags & NCR_F_TEX_FAST) && !(cmd->flags & NCR_F_CLIP) && fabs(x) < 1e9 && fabs(y) < 1e9) {
+            if (const void* map = texture_tmap(tex, c->dev)) {
+                c->tma_map = map; c->tma_cmd = (int32_t)(c->n - 1);
+                c->tma_x = (int32_t)i0; c->tma_y = (int32_t)j0; c->tma_w = (int32_t)tw; c->tma_h = (int32_t)th;
+                keep_ref(c, tex->tmap);
+            }
+        }
         return;
     }
     i64 l, r, t, b;
@@ -1452,6 +1507,37 @@ double NcrMeasureF64Rate(void) {
     return ncr_measure_f64_rate(0);
 }
 
+// Measurement aid: the rate at which this process can bring frames back, i.e. `streams` concurrent device -> pinned-host
+// copies of `bytes_per_copy` each, repeated `iters` times, on the default device.  Returns bytes per second (0 on failure).
+// Run by every rank at the same time, the sum is the box's aggregate readback ceiling that frame-sharded renders meet.
+double NcrMeasureD2HRate(unsigned long long bytes_per_copy, int streams, int iters) {
+    if (!use_device() || bytes_per_copy == 0 || streams < 1 || iters < 1) return 0.0;
+    streams = std::min(streams, 16);
+    std::vector<cudaStream_t> st((size_t)streams, nullptr);
+    std::vector<void*> dev((size_t)streams, nullptr), host((size_t)streams, nullptr);
+    bool ok = true;
+    for (int k = 0; ok && k < streams; ++k)
+        ok = CK(cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking)) && CK(cudaMalloc(&dev[k], bytes_per_copy)) &&
+             CK(cudaMallocHost(&host[k], bytes_per_copy)) && CK(cudaMemsetAsync(dev[k], k + 1, bytes_per_copy, st[k]));
+    double rate = 0.0;
+    if (ok) {
+        for (int k = 0; k < streams; ++k) cudaMemcpyAsync(host[k], dev[k], bytes_per_copy, cudaMemcpyDeviceToHost, st[k]);   // warm-up
+        for (int k = 0; k < streams; ++k) cudaStreamSynchronize(st[k]);
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int it = 0; it < iters; ++it)
+            for (int k = 0; k < streams; ++k) cudaMemcpyAsync(host[k], dev[k], bytes_per_copy, cudaMemcpyDeviceToHost, st[k]);
+        for (int k = 0; k < streams; ++k) ok = CK(cudaStreamSynchronize(st[k])) && ok;
+        const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (ok && s > 0) rate = (double)bytes_per_copy * streams * iters / s;
+    }
+    for (int k = 0; k < streams; ++k) {
+        if (host[k]) cudaFreeHost(host[k]);
+        if (dev[k]) cudaFree(dev[k]);
+        if (st[k]) cudaStreamDestroy(st[k]);
+    }
+    return rate;
+}
+
 int NcrRerunLastFlushEx(RenderContext* ctx, int iters, int flush_l2, float* ms_out, int write_fb, int prefetch) {
     NcrContext* c = live(ctx);
     if (!c || !c->has_last || !use_ctx(c)) return -1;
@@ -1468,8 +1554,8 @@ int NcrRerunLastFlushEx(RenderContext* ctx, int iters, int flush_l2, float* ms_o
         cudaEventRecord(c->ev_t0, c->stream);
         ncr_launch_flush(&R, c->stream, c->ev);
         cudaEventRecord(c->ev_t1, c->stream);
-        g_launches += 3;
-        c->stats.kernel_launches += 3;
+        g_launches += 2u + (R.coarse_list ? 1u : 0u) + (R.yuv_out ? 1u : 0u);
+        c->stats.kernel_launches += 2u + (R.coarse_list ? 1u : 0u) + (R.yuv_out ? 1u : 0u);
         if (!CK(cudaStreamSynchronize(c->stream))) { c->failed = true; return -1; }
         if (ms_out) {
             float* o = ms_out + 4 * it;

@@ -35,23 +35,43 @@ __device__ __noinline__ double ncr_sqrt(double a) { return __dsqrt_rn(a); }
 // shared address is a single byte permute of (texel, lane*8): byte 1 <- texel byte, byte 0 <- lane*8.
 #define NCR_LUT_COPIES 32
 #define NCR_LUT_BYTES (256 * NCR_LUT_COPIES * 8)
-#define NCR_SMEM_BYTES (NCR_LUT_BYTES + (NCR_COMPOSITE_THREADS / 32) * 2 * (int)sizeof(NcrCmd))
+// NCR_TMA_IDENT (experiment X5): per warp two 16x8-texel boxes (512 B each, 128-byte aligned) + two mbarriers
+#ifdef NCR_TMA_IDENT
+#define NCR_TMA_BYTES_PER_WARP (2 * 512 + 128)
+#else
+#define NCR_TMA_BYTES_PER_WARP 0
+#endif
+#define NCR_CMD_SLOT_BYTES ((NCR_COMPOSITE_THREADS / 32) * 2 * (int)sizeof(NcrCmd))
+#define NCR_TMA_OFFSET ((NCR_LUT_BYTES + NCR_CMD_SLOT_BYTES + 127) & ~127)
+#define NCR_SMEM_BYTES (NCR_TMA_OFFSET + (NCR_COMPOSITE_THREADS / 32) * NCR_TMA_BYTES_PER_WARP)
 #ifndef NCR_COMPOSITE_THREADS
 #define NCR_COMPOSITE_THREADS 384
 #endif
 // Pixel slots per lane: NCR_NX columns x 2 rows of 8x4 blocks.  NX=2: a warp owns a 16x8 half-tile (4 px per lane);
 // NX=1: an 8x8 quarter-tile (2 px per lane: half the register state, twice the warps per tile).
-#ifndef NCR_NX
+// NCR_ROW4 (experiment X5, profiles/README.md; not the shipped layout): a lane owns FOUR HORIZONTALLY CONTIGUOUS pixels of one
+// row (lane = (lx 0..3, ly 0..7)), so that 1:1 identity-path texels are one 128-bit load and the RGBA8 frame one 128-bit store
+// per lane.  The region stays 16x8, so ncr_bin_fine's lists are unchanged.
+#ifdef NCR_ROW4
+#define NCR_NX 4
+#define NCR_NY 1
+#define NCR_LANE_X(lane) ((lane) & 3)
+#define NCR_LANE_Y(lane) ((lane) >> 2)
+#define NCR_SLOT_X(lx, k) (4 * (lx) + (k))
+#define NCR_SLOT_Y(ly, k) (ly)
+#else
 #define NCR_NX 2
-#endif
-#ifndef NCR_NY
 #define NCR_NY 2
+#define NCR_LANE_X(lane) ((lane) & 7)
+#define NCR_LANE_Y(lane) ((lane) >> 3)
+#define NCR_SLOT_X(lx, k) (8 * (k) + (lx))
+#define NCR_SLOT_Y(ly, k) (4 * (k) + (ly))
 #endif
-static_assert(NCR_NX == 2 && NCR_NY == 2, "ncr_bin_fine writes lists for 16x8 regions: 4 pixel slots per lane");
-#define NCR_RH (4 * NCR_NY)                      // region height in pixels
-#define NCR_P (NCR_NX * NCR_NY)
-#define NCR_RW (8 * NCR_NX)                      // region width in pixels
-#define NCR_TASKS_PER_TILE ((16 / NCR_RW) * (16 / (4 * NCR_NY)))   // regions per 16x16 tile
+#define NCR_RH NCR_REGION_H                      // region height in pixels (ncr_bin_fine writes lists for 16x8 regions)
+#define NCR_P (NCR_NX * NCR_NY)                  // 4 pixel slots per lane
+#define NCR_RW NCR_REGION_W                      // region width in pixels
+static_assert(NCR_P == 4, "four pixel slots per lane");
+#define NCR_TASKS_PER_TILE NCR_REGIONS_PER_TILE  // regions per 16x16 tile
 #define SX(p) ((p) % NCR_NX)
 #define SY(p) ((p) / NCR_NX)
 #ifndef NCR_COMPOSITE_MIN_CTAS
@@ -337,7 +357,7 @@ __device__ __forceinline__ void tex_fast(const NcrCmd& c, const uint32_t op, con
 template <bool ALPHA, bool COUNT>
 __device__ __forceinline__ bool apply_interior(const NcrCmd& c, const Slots& S, const double* lut, uint32_t lut_base,
                                                double (&dr)[NCR_P], double (&dg)[NCR_P], double (&db)[NCR_P], double (&da)[NCR_P],
-                                               unsigned long long& n_applied) {
+                                               unsigned long long& n_applied, const uint32_t* tbox = nullptr, int tbox_at = 0) {
     const uint32_t op = c.op, flags = c.flags;
     bool in[NCR_P];
     FOR4 in[p] = true;
@@ -379,7 +399,25 @@ __device__ __forceinline__ bool apply_interior(const NcrCmd& c, const Slots& S, 
 #pragma unroll
         for (int k = 0; k < NCR_NY; ++k) yi[k] = __vimin_s32_relu(__double2int_rz(MUL(SUB(S.fy[k], cy), sy)), th2) * tw;
         uint32_t tx[NCR_P];
-        FOR4 tx[p] = __ldg(t32 + (yi[SY(p)] + xi[SX(p)]));
+#ifdef NCR_TMA_IDENT
+        if (tbox) {   // experiment X5: the region's 16x8 texel box was staged in shared memory by the TMA unit
+            FOR4 tx[p] = tbox[tbox_at + NCR_SLOT_Y(0, SY(p)) * NCR_RW + NCR_SLOT_X(0, SX(p))];
+            if (flags & NCR_F_CT_RGB_ONE) shade_rgba8<ALPHA, COUNT, true>(c, lut_base, tx, in, dr, dg, db, da, n_applied);
+            else shade_rgba8<ALPHA, COUNT, false>(c, lut_base, tx, in, dr, dg, db, da, n_applied);
+            return true;
+        }
+#endif
+#ifdef NCR_ROW4
+        // 1:1 sampling without clamping: the lane's four texels are contiguous; one 128-bit load when they are 16-byte aligned
+        const int t0 = yi[0] + xi[0];
+        if (xi[3] == xi[0] + 3 && (t0 & 3) == 0) {
+            const uint4 q = __ldg((const uint4*)(t32 + t0));
+            tx[0] = q.x; tx[1] = q.y; tx[2] = q.z; tx[3] = q.w;
+        } else
+#endif
+        {
+            FOR4 tx[p] = __ldg(t32 + (yi[SY(p)] + xi[SX(p)]));
+        }
         if (flags & NCR_F_CT_RGB_ONE) shade_rgba8<ALPHA, COUNT, true>(c, lut_base, tx, in, dr, dg, db, da, n_applied);
         else shade_rgba8<ALPHA, COUNT, false>(c, lut_base, tx, in, dr, dg, db, da, n_applied);
         return true;
@@ -511,12 +549,18 @@ __device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A
             u[p] = MUL(SUB(fi, c.x), c.sx);
             v[p] = MUL(SUB(fj, c.y), c.sy);
         }
-    } else if (op == NCR_OP_TEX_PERSP) {   // extension: row-major 3x3 inverse homography, then cpp:765-771
+    } else if (op == NCR_OP_TEX_PERSP) {   // extension (this repo's own spec): row-major 3x3 inverse homography, one reciprocal
+        // of the homogeneous w per pixel and two multiplies, then cpp:765-771.  The per-column / per-row products are hoisted.
+        double hx[NCR_NX], ax[NCR_NX], bx[NCR_NX], hy[NCR_NY], ay[NCR_NY], by[NCR_NY];
+#pragma unroll
+        for (int k = 0; k < NCR_NX; ++k) { hx[k] = MUL(c.p[0], S.fx[k]); ax[k] = MUL(c.inv[0], S.fx[k]); bx[k] = MUL(c.inv[3], S.fx[k]); }
+#pragma unroll
+        for (int k = 0; k < NCR_NY; ++k) { hy[k] = MUL(c.p[1], S.fy[k]); ay[k] = MUL(c.inv[1], S.fy[k]); by[k] = MUL(c.inv[4], S.fy[k]); }
         FOR4 {
-            const double fi = S.fx[SX(p)], fj = S.fy[SY(p)];
-            const double hw = ADD(ADD(MUL(c.p[0], fi), MUL(c.p[1], fj)), c.p[2]);
-            const double Xp = DIV(ADD(ADD(MUL(c.inv[0], fi), MUL(c.inv[1], fj)), c.inv[2]), hw);
-            const double Yp = DIV(ADD(ADD(MUL(c.inv[3], fi), MUL(c.inv[4], fj)), c.inv[5]), hw);
+            const double hw = ADD(ADD(hx[SX(p)], hy[SY(p)]), c.p[2]);
+            const double rw = DIV(1.0, hw);
+            const double Xp = MUL(ADD(ADD(ax[SX(p)], ay[SY(p)]), c.inv[2]), rw);
+            const double Yp = MUL(ADD(ADD(bx[SX(p)], by[SY(p)]), c.inv[5]), rw);
             in[p] = in[p] && hw > 0.0 && !(Xp < c.x) && !(Xp > c.xw) && !(Yp < c.y) && !(Yp > c.yh);
             u[p] = MUL(SUB(Xp, c.x), c.sx);
             v[p] = MUL(SUB(Yp, c.y), c.sy);
@@ -570,6 +614,33 @@ __device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A
     }
 }
 
+#ifdef NCR_TMA_IDENT
+// ---- experiment X5: TMA staging of a region's texel box (cp.async.bulk.tensor.2d + mbarrier), see profiles/README.md ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_mbar_init(uint32_t mbar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+}
+// one elected lane: expect 512 bytes, then start the bulk tensor copy of the 16x8 box whose first texel is (u0, v0)
+__device__ __forceinline__ void tma_load_box(uint32_t dst, const void* map, int u0, int v0, uint32_t mbar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 512;" ::"r"(mbar) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(u0), "r"(v0), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void tma_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}"
+                 ::"r"(mbar), "r"(parity) : "memory");
+}
+// Can region `task` take its background texels from a TMA box?  (no clamping anywhere in the region: cpp:560-563 are no-ops)
+__device__ __forceinline__ bool tma_region_ok(const NcrFlushArgs& A, int task, int& u0, int& v0) {
+    const int tile = task / NCR_TASKS_PER_TILE, sub = task % NCR_TASKS_PER_TILE;
+    const int x0 = (tile % A.d.tiles_x) * NCR_TILE, y0 = (tile / A.d.tiles_x) * NCR_TILE + sub * NCR_RH;
+    u0 = x0 - A.tma_x;
+    v0 = y0 - A.tma_y;
+    return A.tma_map != nullptr && u0 >= 0 && v0 >= 0 && u0 + NCR_RW - 1 <= A.tma_w - 2 && v0 + NCR_RH - 1 <= A.tma_h - 2 &&
+           x0 + NCR_RW <= A.d.w && y0 + NCR_RH <= A.d.h;
+}
+#endif
+
 // Copies command `e` (list entry) from HBM into a per-warp shared slot: 15 lanes x 16 bytes.
 __device__ __forceinline__ void stage_cmd(const NcrFlushArgs& A, NcrCmd* dst, uint32_t e, int lane) {
     constexpr uint32_t WORDS = NCR_CMD_WORDS16;   // 15 x 16 B
@@ -578,20 +649,22 @@ __device__ __forceinline__ void stage_cmd(const NcrFlushArgs& A, NcrCmd* dst, ui
 }
 
 // One region (16x8 px) composited by one warp: pixel set-up, optional canvas read, the region's command list in submission
-// order, write-back (f64 canvas unless write_fb == 0, fused u8 image, fused YUV planes).
+// order, write-back (f64 canvas unless write_fb == 0, fused u8 image).
 //   ents       the first 32 entries of the region's list, one per lane (already loaded);
 //   slot       in/out: which of the warp's two shared command slots holds the command to run next;
 //   have_cmd0  the region's first command is already staged in s_cmd[slot] (cross-region prefetch);
-//   next_valid / next_e0   cross-region prefetch: the first list entry of the region this warp composites next; its command is
-//              fetched while this region's last command is applied.  Returns true when that command is staged in s_cmd[slot].
+//   next_valid / next_ents   cross-region prefetch: the first list entries (one per lane) of the region this warp composites
+//              next; its first command is fetched while this region's last command is applied (the entries were loaded a whole
+//              region earlier and are only touched then).  Returns true when that command is staged in s_cmd[slot].
 template <bool ALPHA, bool COUNT>
 __device__ __forceinline__ bool run_region(const NcrFlushArgs& A, NcrCmd (*s_cmd)[2], const int task, const uint32_t loff,
                                            const uint32_t lcount, uint32_t ents, int& slot, const bool have_cmd0,
-                                           const bool next_valid, const uint32_t next_e0, const double* lut,
-                                           unsigned long long& n_applied) {
+                                           const bool next_valid, const uint32_t next_ents, const double* lut,
+                                           unsigned long long& n_applied, const uint32_t* tbox = nullptr, uint32_t tbox_mbar = 0,
+                                           uint32_t tbox_parity = 0, bool* tbox_used = nullptr) {
     const int lane = threadIdx.x & 31;
     const uint32_t lut_base = (uint32_t)lane * 8u;
-    const int lx = lane & 7, ly = lane >> 3;
+    const int lx = NCR_LANE_X(lane), ly = NCR_LANE_Y(lane);
     constexpr int IPP = ALPHA ? 4 : 3;
     constexpr uint32_t WORDS = NCR_CMD_WORDS16;
     const int W = A.d.w, H = A.d.h;
@@ -599,15 +672,15 @@ __device__ __forceinline__ bool run_region(const NcrFlushArgs& A, NcrCmd (*s_cmd
     const int tile = task / NCR_TASKS_PER_TILE, sub = task % NCR_TASKS_PER_TILE;
     const int x0 = (tile % A.d.tiles_x) * NCR_TILE + (sub % (16 / NCR_RW)) * NCR_RW;
     const int y0 = (tile / A.d.tiles_x) * NCR_TILE + (sub / (16 / NCR_RW)) * NCR_RH;
-    if ((lcount == 0 && A.u8_out == nullptr && A.yuv_out == nullptr) || y0 >= H || x0 >= W) {   // nothing to do here
-        if (next_valid) stage_cmd(A, &s_cmd[0][slot], next_e0, lane);
+    if ((lcount == 0 && A.u8_out == nullptr) || y0 >= H || x0 >= W) {   // nothing to do here
+        if (next_valid) stage_cmd(A, &s_cmd[0][slot], __shfl_sync(FULL, next_ents, 0), lane);
         return next_valid;
     }
     Slots S;
 #pragma unroll
-    for (int k = 0; k < NCR_NX; ++k) { S.xs[k] = x0 + 8 * k + lx; S.fx[k] = (double)S.xs[k]; }
+    for (int k = 0; k < NCR_NX; ++k) { S.xs[k] = x0 + NCR_SLOT_X(lx, k); S.fx[k] = (double)S.xs[k]; }
 #pragma unroll
-    for (int k = 0; k < NCR_NY; ++k) { S.ys[k] = y0 + 4 * k + ly; S.fy[k] = (double)S.ys[k]; }
+    for (int k = 0; k < NCR_NY; ++k) { S.ys[k] = y0 + NCR_SLOT_Y(ly, k); S.fy[k] = (double)S.ys[k]; }
     bool valid[NCR_P];
     FOR4 valid[p] = S.xs[SX(p)] < W && S.ys[SY(p)] < H;
 
@@ -632,18 +705,27 @@ __device__ __forceinline__ bool run_region(const NcrFlushArgs& A, NcrCmd (*s_cmd
     uint32_t cur = __shfl_sync(FULL, ents, 0);
     if (lcount != 0 && !have_cmd0) stage_cmd(A, &s_cmd[0][slot], cur, lane);
     bool staged_next = false;
-    if (lcount == 0 && next_valid) { stage_cmd(A, &s_cmd[0][slot], next_e0, lane); staged_next = true; }
+    if (lcount == 0 && next_valid) { stage_cmd(A, &s_cmd[0][slot], __shfl_sync(FULL, next_ents, 0), lane); staged_next = true; }
     for (uint32_t k = 0; k < lcount; ++k) {
         const bool more = k + 1 < lcount;
-        uint32_t nxt = next_e0;
+        uint32_t nxt = 0;
         if (more) {
             if (((k + 1) & 31u) == 0u) ents = (k + 1 + lane < lcount) ? __ldg(list + loff + k + 1 + lane) : 0u;   // next 32 entries
             nxt = __shfl_sync(FULL, ents, (k + 1) & 31);
+        } else if (next_valid) {
+            nxt = __shfl_sync(FULL, next_ents, 0);
         }
         const bool fetch = more || next_valid;
         uint4 pre = make_uint4(0, 0, 0, 0);
         if (fetch && lane < (int)WORDS) pre = __ldg((const uint4*)(A.cmds + (nxt & NCR_ENTRY_INDEX)) + lane);   // in flight during the apply
         const NcrCmd& c = s_cmd[0][slot];
+#ifdef NCR_TMA_IDENT
+        if (tbox && cur == ((uint32_t)A.tma_cmd | NCR_ENTRY_INTERIOR)) {   // the staged box belongs to this command
+            tma_wait(tbox_mbar, tbox_parity);
+            *tbox_used = true;
+            apply_interior<ALPHA, COUNT>(c, S, lut, lut_base, dr, dg, db, da, n_applied, tbox, ly * NCR_RW + lx);
+        } else
+#endif
         if (!(cur & NCR_ENTRY_INTERIOR) || !apply_interior<ALPHA, COUNT>(c, S, lut, lut_base, dr, dg, db, da, n_applied))
             apply_cmd<ALPHA, COUNT>(c, A, S, lut, lut_base, dr, dg, db, da, n_applied);
         if (fetch && lane < (int)WORDS) ((uint4*)&s_cmd[0][slot ^ 1])[lane] = pre;
@@ -654,6 +736,18 @@ __device__ __forceinline__ bool run_region(const NcrFlushArgs& A, NcrCmd (*s_cmd
     }
 
     // region write-back: canonical f64 canvas (only if something was drawn, and not for a present-only flush) and the fused (iu8)(v*255) image
+#ifdef NCR_ROW4
+    bool u8_done = false;
+    if (ALPHA && A.u8_out && valid[3] && (W & 3) == 0) {   // the lane's four RGBA8 pixels: one 128-bit store
+        uint32_t o[4];
+        FOR4 o[p] = (uint32_t)ncr_to_u8(dr[p]) | ((uint32_t)ncr_to_u8(dg[p]) << 8) | ((uint32_t)ncr_to_u8(db[p]) << 16) |
+                    ((uint32_t)ncr_to_u8(da[p]) << 24);
+        *(uint4*)((uint32_t*)A.u8_out + (size_t)S.ys[0] * W + S.xs[0]) = make_uint4(o[0], o[1], o[2], o[3]);
+        u8_done = true;
+    }
+#else
+    const bool u8_done = false;
+#endif
     FOR4 if (valid[p]) {
         const size_t pix = ((size_t)S.ys[SY(p)] * W + S.xs[SX(p)]) * IPP;
         if (lcount != 0 && A.write_fb) {
@@ -665,7 +759,7 @@ __device__ __forceinline__ bool run_region(const NcrFlushArgs& A, NcrCmd (*s_cmd
                 q[0] = dr[p]; q[1] = dg[p]; q[2] = db[p];
             }
         }
-        if (A.u8_out) {
+        if (A.u8_out && !u8_done) {
             if (ALPHA) {
                 const uint32_t o = (uint32_t)ncr_to_u8(dr[p]) | ((uint32_t)ncr_to_u8(dg[p]) << 8) |
                                    ((uint32_t)ncr_to_u8(db[p]) << 16) | ((uint32_t)ncr_to_u8(da[p]) << 24);
@@ -676,50 +770,16 @@ __device__ __forceinline__ bool run_region(const NcrFlushArgs& A, NcrCmd (*s_cmd
             }
         }
     }
-    // Present path, fused: the YUV 4:2:0 planes of the (iu8)(v*255) image, same arithmetic as ncr_yuv420p
-    // (kernels.cu).  A 2x2 chroma block is (lane, lane^1) x (lane, lane^8) of the same pixel slot — region origins are
-    // even — so the block sums are two shuffles of the packed 10-bit channel sums; a missing neighbour column / row
-    // (odd canvas size) is replaced by the pixel's own, which is the edge replication of the standalone kernel.
-    if (A.yuv_out) {   // warp-uniform
-        const int cw = (W + 1) >> 1, chh = (H + 1) >> 1;
-        unsigned char* const Yp = A.yuv_out;
-        unsigned char* const Up = Yp + (size_t)W * H;
-        unsigned char* const Vp = Up + (size_t)cw * chh;
-        FOR4 {
-            const int x = S.xs[SX(p)], y = S.ys[SY(p)];
-            const int r = ncr_to_u8(dr[p]), g = ncr_to_u8(dg[p]), b = ncr_to_u8(db[p]);
-            if (valid[p]) Yp[(size_t)y * W + x] = (unsigned char)(((66 * r + 129 * g + 25 * b + 128) >> 8) + 16);
-            const uint32_t pk = (uint32_t)r | ((uint32_t)g << 10) | ((uint32_t)b << 20);
-            const uint32_t side = __shfl_xor_sync(FULL, pk, 1);
-            const uint32_t row = pk + (((x ^ 1) < W) ? side : pk);
-            const uint32_t other = __shfl_xor_sync(FULL, row, 8);
-            const uint32_t sum = row + (((y ^ 1) < H) ? other : row);
-            if (valid[p] && !((x | y) & 1)) {
-                const int mr = (int)((sum & 1023u) + 2u) >> 2, mg = (int)(((sum >> 10) & 1023u) + 2u) >> 2,
-                          mb = (int)((sum >> 20) + 2u) >> 2;
-                const size_t ci = (size_t)(y >> 1) * cw + (x >> 1);
-                Up[ci] = (unsigned char)(((-38 * mr - 74 * mg + 112 * mb + 128) >> 8) + 128);
-                Vp[ci] = (unsigned char)(((112 * mr - 94 * mg - 18 * mb + 128) >> 8) + 128);
-            }
-        }
-    }
     return staged_next;
-}
-
-// Claims the next region (dynamic scheduling: one global counter).  `atom.inc` is used instead of atomicAdd so that ptxas does
-// not turn the claim into its warp-aggregated form, whose result shuffle would make the warp wait for the atomic right here.
-__device__ __forceinline__ uint32_t claim_region(uint32_t* counter) {
-    uint32_t t;
-    asm volatile("atom.global.inc.u32 %0, [%1], 0xffffffff;" : "=r"(t) : "l"(counter) : "memory");
-    return t;
 }
 
 // PREFETCH = false: claim a region, read its header and list, composite it (the in-region command prefetch is the only
 // look-ahead) — the variant for long lists, where the per-region latency chain is amortised over many commands.
-// PREFETCH = true: the variant for short lists (chart / video frames: a handful of commands per region), where that chain
-// (claim -> header -> list -> first command, four dependent round trips to L2) is most of a region's time.  The chain of
-// region t+1 runs while region t is composited: the claim for t+2 is issued at the start of t and consumed at its end; the
-// header of t+1 is loaded at the end of t-1, its list entries at the start of t, its first command during t's last command.
+// PREFETCH = true: the variant for very short lists (a few full-screen commands per region), where that chain
+// (claim -> header -> list -> first command, four dependent round trips to L2) is most of a region's time: regions are
+// assigned statically and the rest of the chain is software-pipelined over regions, each link issued one whole region before
+// its result is needed.  (A dynamic claim carried across a region was measured first: its result register is spilled right
+// after the atomic — the warp waits there — and pinning it any other way costs what it saves; profiles/README.md.)
 template <bool ALPHA, bool COUNT, bool PREFETCH>
 __global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, NCR_COMPOSITE_MIN_CTAS) ncr_composite(NcrFlushArgs A) {
     // u8 / 255.0 (CreateTextureUInt8, cpp:350), IEEE division on both sides.  32 copies, copy c of entry k at [k*32 + c]:
@@ -743,42 +803,79 @@ __global__ void __launch_bounds__(NCR_COMPOSITE_THREADS, NCR_COMPOSITE_MIN_CTAS)
     unsigned long long n_applied = 0;
     int slot = 0;
 
+    const uint32_t n = (uint32_t)n_tasks;
+    const uint32_t n_warps = gridDim.x * (NCR_COMPOSITE_THREADS / 32);
+    const uint32_t gwarp = blockIdx.x * (NCR_COMPOSITE_THREADS / 32) + warp;
     if (!PREFETCH) {
-        for (;;) {
-            int task = 0;
-            if (lane == 0) task = (int)atomicAdd(&A.cursors[5], 1u);
-            task = __shfl_sync(FULL, task, 0);
-            if (task >= n_tasks) break;
+        // Dynamic scheduling: a warp's first region is its own index (no claim: 1,776 simultaneous atomics on one address cost
+        // microseconds at kernel start); every later one is claimed from the global counter, which counts from n_warps.
+        uint32_t task = gwarp;
+        while (task < n) {
             const uint2 h = __ldg(hdr + task);
             uint32_t ents = 0;
             if ((uint32_t)lane < h.y) ents = __ldg(A.fine_list + h.x + lane);   // first 32 entries, one coalesced load
-            run_region<ALPHA, COUNT>(A, s_cmd, task, h.x, h.y, ents, slot, false, false, 0u, s_lut, n_applied);
+            run_region<ALPHA, COUNT>(A, s_cmd, (int)task, h.x, h.y, ents, slot, false, false, 0u, s_lut, n_applied);
+            if (lane == 0) task = atomicAdd(&A.cursors[5], 1u) + n_warps;
+            task = __shfl_sync(FULL, task, 0);
         }
     } else {
-        uint32_t t_cur = 0, t_nxt = 0;
-        if (lane == 0) { t_cur = claim_region(&A.cursors[5]); t_nxt = claim_region(&A.cursors[5]); }
-        t_cur = __shfl_sync(FULL, t_cur, 0);
-        t_nxt = __shfl_sync(FULL, t_nxt, 0);
-        uint2 h_cur = make_uint2(0, 0), h_nxt = make_uint2(0, 0);
-        if (t_cur < (uint32_t)n_tasks) h_cur = __ldg(hdr + t_cur);
-        if (t_nxt < (uint32_t)n_tasks) h_nxt = __ldg(hdr + t_nxt);
-        uint32_t e_cur = 0;
-        if ((uint32_t)lane < h_cur.y) e_cur = __ldg(A.fine_list + h_cur.x + lane);
+        // Static round-robin (region r -> warp r mod n_warps; neighbouring regions go to different SMs, so a hot spot of the
+        // frame is spread over the machine) and a software pipeline over regions, one stage per region's worth of work between
+        // a load's issue and its first use:
+        //   iteration i (compositing region R[i]) issues  header(R[i+2]),  entries(R[i+1])
+        //   and uses, in its last command, entries(R[i+1]) to fetch that region's first command.
+        // No claim at all: this variant only runs frames whose lists are short (host: A.prefetch), where regions cost about the same.
+        uint32_t t0 = gwarp, t1 = gwarp + n_warps, t2 = gwarp + 2 * n_warps;
+        uint2 h0 = make_uint2(0, 0), h1 = make_uint2(0, 0);
+        if (t0 < n) h0 = __ldg(hdr + t0);
+        if (t1 < n) h1 = __ldg(hdr + t1);
+        uint32_t e0 = 0;
+        if ((uint32_t)lane < h0.y) e0 = __ldg(A.fine_list + h0.x + lane);
         bool have0 = false;
-        while (t_cur < (uint32_t)n_tasks) {
-            uint32_t t_aft = 0;
-            if (lane == 0) t_aft = claim_region(&A.cursors[5]);   // region t+2: in flight for the whole of region t
-            uint32_t e_nxt = 0;
-            if ((uint32_t)lane < h_nxt.y) e_nxt = __ldg(A.fine_list + h_nxt.x + lane);   // h_nxt is {0,0} past the end
-            const bool next_valid = h_nxt.y != 0;
-            const uint32_t next_e0 = __shfl_sync(FULL, e_nxt, 0);
-            have0 = run_region<ALPHA, COUNT>(A, s_cmd, (int)t_cur, h_cur.x, h_cur.y, e_cur, slot, have0, next_valid, next_e0,
-                                             s_lut, n_applied);
-            t_cur = t_nxt; h_cur = h_nxt; e_cur = e_nxt;
-            asm volatile("" : "+r"(t_aft) :: "memory");   // the claim's result is first needed here, after the region's stores
-            t_nxt = __shfl_sync(FULL, t_aft, 0);
-            h_nxt = make_uint2(0, 0);
-            if (t_nxt < (uint32_t)n_tasks) h_nxt = __ldg(hdr + t_nxt);
+#ifdef NCR_TMA_IDENT
+        // experiment X5: the background texel box of region R[i+1] is staged by the TMA unit while region R[i] is composited
+        unsigned char* tma_base = ncr_smem + NCR_TMA_OFFSET + warp * NCR_TMA_BYTES_PER_WARP;
+        const uint32_t mbar0 = smem_u32(tma_base + 1024);
+        if (lane == 0) { tma_mbar_init(mbar0); tma_mbar_init(mbar0 + 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+        uint32_t parity = 0, inflight = 0, it = 0;   // bit b: state of buffer b
+        {
+            int u0, v0;
+            if (t0 < n && tma_region_ok(A, (int)t0, u0, v0)) {
+                if (lane == 0) tma_load_box(smem_u32(tma_base), A.tma_map, u0, v0, mbar0);
+                inflight |= 1u;
+            }
+        }
+#endif
+        while (t0 < n) {
+            uint2 h2 = make_uint2(0, 0);
+            if (t2 < n) h2 = __ldg(hdr + t2);                              // R[i+2]: first used at the top of the next iteration
+            uint32_t e1 = 0;
+            if ((uint32_t)lane < h1.y) e1 = __ldg(A.fine_list + h1.x + lane);   // R[i+1]: first used in this region's last command
+#ifdef NCR_TMA_IDENT
+            const uint32_t b = it & 1u, nb = b ^ 1u;
+            {   // stage R[i+1]'s box into the other buffer (first drain a box nobody consumed, to keep the barrier's phase)
+                int u0, v0;
+                if (inflight >> nb & 1u) { tma_wait(mbar0 + 8 * nb, parity >> nb & 1u); parity ^= 1u << nb; inflight &= ~(1u << nb); }
+                if (t1 < n && tma_region_ok(A, (int)t1, u0, v0)) {
+                    if (lane == 0) tma_load_box(smem_u32(tma_base + 512 * nb), A.tma_map, u0, v0, mbar0 + 8 * nb);
+                    inflight |= 1u << nb;
+                }
+            }
+            bool used = false;
+            const bool have_box = (inflight >> b & 1u) != 0;
+            have0 = run_region<ALPHA, COUNT>(A, s_cmd, (int)t0, h0.x, h0.y, e0, slot, have0, h1.y != 0, e1, s_lut, n_applied,
+                                             have_box ? (const uint32_t*)(tma_base + 512 * b) : nullptr, mbar0 + 8 * b, parity >> b & 1u, &used);
+            if (used) { parity ^= 1u << b; inflight &= ~(1u << b); }
+            __syncwarp();   // every lane has read its texels before the buffer is reused two iterations later
+            ++it;
+#else
+            have0 = run_region<ALPHA, COUNT>(A, s_cmd, (int)t0, h0.x, h0.y, e0, slot, have0, h1.y != 0, e1, s_lut, n_applied);
+#endif
+            t0 = t1; t1 = t2; t2 += n_warps;
+            h0 = h1; h1 = h2;
+            e0 = e1;
         }
     }
 

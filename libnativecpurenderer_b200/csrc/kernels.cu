@@ -33,7 +33,14 @@ __device__ __forceinline__ bool box_hits(const NcrBox& bx, int x0, int y0, int x
 // masks fit (n_cmds / 8 bits per CTA).
 extern __shared__ uint32_t ncr_coarse_masks[];
 #define NCR_COARSE_U 8
-#define NCR_FINE_U 4
+// Measured on B200 (profiles/README.md): 2 chains per lane at 4 CTAs per SM (<= 64 registers) beats 4 chains at 3 CTAs by 15-20 %
+// on every workload; 8 chains is slower than 4.
+#ifndef NCR_FINE_U
+#define NCR_FINE_U 2
+#endif
+#ifndef NCR_FINE_MIN_CTAS
+#define NCR_FINE_MIN_CTAS 4
+#endif
 
 #define NCR_COARSE_WARPS 8   // warps per bin: the command range is cut into this many contiguous segments
 __global__ void __launch_bounds__(32 * NCR_COARSE_WARPS) ncr_bin_coarse(NcrFlushArgs A, int use_masks, uint32_t mask_words) {
@@ -133,7 +140,7 @@ __global__ void __launch_bounds__(32 * NCR_COARSE_WARPS) ncr_bin_coarse(NcrFlush
 // atomicAdd carves the tile's two runs out of the list array and the staged entries are copied out coalesced.  A region with
 // more hits than the stage holds re-scans and writes directly (second pass).
 #define NCR_FINE_STAGE 320
-__global__ void __launch_bounds__(256) ncr_bin_fine(NcrFlushArgs A) {
+__global__ void __launch_bounds__(256, NCR_FINE_MIN_CTAS) ncr_bin_fine(NcrFlushArgs A) {
     __shared__ uint32_t s_stage[8][2][NCR_FINE_STAGE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile = blockIdx.x * 8 + warp;
@@ -142,8 +149,10 @@ __global__ void __launch_bounds__(256) ncr_bin_fine(NcrFlushArgs A) {
     const int tx = tile % A.d.tiles_x, ty = tile / A.d.tiles_x;
     const int x0 = tx * NCR_TILE, y0 = ty * NCR_TILE, x1 = x0 + NCR_TILE, y1 = y0 + NCR_TILE;
     const int bin = (ty / NCR_COARSE) * A.d.bins_x + tx / NCR_COARSE;
-    const uint32_t cbase = A.coarse_off[bin];
-    const uint32_t ccount = A.coarse_off[A.d.bins_x * A.d.bins_y + bin];
+    // small batches skip the coarse pass: every command is a candidate (direct == true, the "list" is the identity)
+    const bool direct = A.coarse_list == nullptr;
+    const uint32_t cbase = direct ? 0u : A.coarse_off[bin];
+    const uint32_t ccount = direct ? A.n_cmds : A.coarse_off[A.d.bins_x * A.d.bins_y + bin];
     const int r0 = tile * NCR_REGIONS_PER_TILE;
 
     if (ccount == 0) {
@@ -153,13 +162,17 @@ __global__ void __launch_bounds__(256) ncr_bin_fine(NcrFlushArgs A) {
     const uint32_t lt = (1u << lane) - 1u;
     uint32_t cnt[2] = {0, 0};
     uint32_t off[2] = {0, 0};
+    uint32_t n_interior = 0;
     for (int pass = 0; pass < 2; ++pass) {
         uint32_t pos[2] = {0, 0};
         for (uint32_t k = 0; k < ccount; k += 32 * NCR_FINE_U) {
             uint32_t idx[NCR_FINE_U], code[NCR_FINE_U];
             int4 bxs[NCR_FINE_U];
 #pragma unroll
-            for (int u = 0; u < NCR_FINE_U; ++u) idx[u] = A.coarse_list[cbase + min(k + u * 32 + lane, ccount - 1)];   // clamped, unconditional
+            for (int u = 0; u < NCR_FINE_U; ++u) {
+                const uint32_t at = min(k + u * 32 + lane, ccount - 1);   // clamped, unconditional
+                idx[u] = direct ? at : A.coarse_list[cbase + at];
+            }
 #pragma unroll
             for (int u = 0; u < NCR_FINE_U; ++u) bxs[u] = __ldg((const int4*)&A.boxes[idx[u]]);
 #pragma unroll
@@ -174,6 +187,7 @@ __global__ void __launch_bounds__(256) ncr_bin_fine(NcrFlushArgs A) {
                 for (int h = 0; h < 2; ++h) {
                     const uint32_t cd = (code[u] >> (2 * h)) & 3u;
                     const uint32_t m = __ballot_sync(0xffffffffu, cd != 0u);
+                    n_interior += (pass == 0 && cd == 2u) ? 1u : 0u;   // per lane; reduced once per tile (statistics)
                     if (cd) {
                         const uint32_t at = pos[h] + __popc(m & lt);
                         const uint32_t e = idx[u] | (cd == 2u ? NCR_ENTRY_INTERIOR : 0u);
@@ -187,9 +201,15 @@ __global__ void __launch_bounds__(256) ncr_bin_fine(NcrFlushArgs A) {
         if (pass == 1) return;
         cnt[0] = pos[0]; cnt[1] = pos[1];
         uint32_t base = 0, total = cnt[0] + cnt[1];
+        if (A.count_pixels) {   // stats mode only: how many entries were proven interior
+            for (int sft = 16; sft > 0; sft >>= 1) n_interior += __shfl_down_sync(0xffffffffu, n_interior, sft);
+        } else {
+            n_interior = 0;
+        }
         if (lane == 0) {
             base = total ? atomicAdd(&A.cursors[1], total) : 0u;
             if (base + total > A.fine_cap) { total = 0; atomicExch(&A.cursors[4], 2u); }
+            if (n_interior) atomicAdd(&A.cursors[6], n_interior);   // statistics only
         }
         base = __shfl_sync(0xffffffffu, base, 0);
         total = __shfl_sync(0xffffffffu, total, 0);
@@ -217,45 +237,94 @@ __global__ void __launch_bounds__(256) ncr_convert_u8(const double* __restrict__
 }
 
 // Present path: the (iu8)(v*255) image -> planar YUV 4:2:0, the format PutRendererContextFrame hands to the
-// encoder (reference cpp:232-256: f64 -> u8 truncation, then sws_scale to AV_PIX_FMT_YUV420P).  libswscale is a third-party
-// dependency that is absent here, so its exact rounding cannot be pinned ("parity unpinned"); this kernel implements the
-// published BT.601 studio-swing integer matrix (the 8-bit-shift coefficients of swscale's own rgb24toyv12 C path):
-//     Y = ((66 R + 129 G + 25 B + 128) >> 8) + 16      for every pixel
-//     U = ((-38 R - 74 G + 112 B + 128) >> 8) + 128    V = ((112 R - 94 G - 18 B + 128) >> 8) + 128
-// with U, V taken from the rounded mean (sum + 2) >> 2 of each 2x2 block (edge blocks of odd-sized images replicate the
-// last column / row).  Alpha is ignored, as AV_PIX_FMT_RGBA -> YUV420P does.  One thread per 2x2 block; 1.5 bytes per pixel
-// leave the GPU instead of 3 or 4.
-template <int IPP>
+// encoder (reference cpp:232-256: f64 -> u8 truncation, then sws_scale(RGBA|RGB24 -> YUV420P, same size, SWS_BILINEAR)).
+// libswscale is an un-vendored third-party dependency of the reference; this kernel computes what libswscale computes for that
+// call on x86-64 (no SWS_ACCURATE_RND: the 16-bit SIMD vertical scaler), restated in oracle/ncr_oracle.c from the published
+// algorithm and pinned bit-exactly to a real build (libswscale 9.1.100; tests/golden/make_swscale_fixtures.py) for even sizes
+// >= 8x8.  Integer arithmetic only:
+//   luma    Y = clip8(((((8414 R + 16519 G + 3208 B + (32 << 14) + (1 << 8)) >> 9) << 1) + 64) >> 7)
+//   chroma  per pixel PAIR (R2 = R[2i] + R[2i+1], ...): U15 = min(((-4865 R2 - 9528 G2 + 14392 B2 + (0x4001 << 9)) >> 10) << 1, 32767),
+//           V15 likewise with (14392, -12061, -2332); vertically taps {512, 1536, 1536, 512} on rows 2c-1 .. 2c+2, taps outside
+//           the image folded onto the edge row; acc = 5 + sum_k ((U15[k] * coeff[k]) >> 16), U = clip8(acc >> 3) — except the last
+//           chroma row, which libswscale produces with its C scaler: U = clip8(((64 << 12) + sum_k U15[k] * coeff[k]) >> 19).
+// One thread per VEC horizontally adjacent chroma samples (VEC = 4: eight pixels per row, 64/128-bit loads, 8-byte luma and
+// 4-byte chroma stores; VEC = 1 for widths that are not multiples of 8).  Only 1.5 bytes per pixel leave the GPU.
+__device__ __forceinline__ unsigned char ncr_clip8(int v) { return (unsigned char)min(max(v, 0), 255); }
+
+template <int IPP, int VEC>
 __global__ void __launch_bounds__(256) ncr_yuv420p(const unsigned char* __restrict__ img, unsigned char* __restrict__ out,
                                                    int w, int h) {
     const int cw = (w + 1) >> 1, ch = (h + 1) >> 1;
-    const int bx = blockIdx.x * 32 + (threadIdx.x & 31), by = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (bx >= cw || by >= ch) return;
+    const int bx = blockIdx.x * 32 + (threadIdx.x & 31), cj = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (bx * VEC >= cw || cj >= ch) return;
     unsigned char* Y = out;
     unsigned char* U = out + (size_t)w * h;
     unsigned char* V = U + (size_t)cw * ch;
-    int sr = 0, sg = 0, sb = 0;
+    // tap rows 2cj-1 .. 2cj+2, out-of-image taps folded onto the edge row (libswscale initFilter)
+    // (static indices only: a run of equal rows keeps its summed coefficient on its first tap, the others get 0 and are skipped)
+    int row[4], coef[4] = {512, 1536, 1536, 512};
 #pragma unroll
-    for (int dy = 0; dy < 2; ++dy) {
+    for (int k = 0; k < 4; ++k) row[k] = min(max(2 * cj - 1 + k, 0), h - 1);
 #pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-            const int x = min(2 * bx + dx, w - 1), y = min(2 * by + dy, h - 1);
-            int r, g, b;
-            if (IPP == 4) {
-                const uint32_t t = __ldg((const uint32_t*)img + (size_t)y * w + x);
-                r = t & 255u; g = (t >> 8) & 255u; b = (t >> 16) & 255u;
-            } else {
-                const unsigned char* q = img + ((size_t)y * w + x) * 3;
-                r = __ldg(q); g = __ldg(q + 1); b = __ldg(q + 2);
+    for (int k = 3; k >= 1; --k)
+        if (row[k] == row[k - 1]) { coef[k - 1] += coef[k]; coef[k] = 0; }
+    const bool last = (cj == ch - 1);
+    int au[VEC], av[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) au[v] = av[v] = last ? (64 << 12) : 5;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (coef[k] == 0) continue;
+        const int y = row[k];
+        __align__(16) unsigned char px[2 * VEC * IPP];
+        if (VEC == 4) {   // w % 8 == 0: 8 pixels, 8-byte aligned
+            const unsigned char* src = img + ((size_t)y * w + 8 * bx) * IPP;
+#pragma unroll
+            for (int q = 0; q < IPP; ++q) ((uint2*)px)[q] = __ldg((const uint2*)src + q);
+        } else {
+            const int x0 = 2 * bx, x1 = min(2 * bx + 1, w - 1);
+#pragma unroll
+            for (int q = 0; q < IPP; ++q) {
+                px[q] = __ldg(img + ((size_t)y * w + x0) * IPP + q);
+                px[IPP + q] = __ldg(img + ((size_t)y * w + x1) * IPP + q);
             }
-            sr += r; sg += g; sb += b;
-            if (2 * bx + dx < w && 2 * by + dy < h)
-                Y[(size_t)y * w + x] = (unsigned char)(((66 * r + 129 * g + 25 * b + 128) >> 8) + 16);
+        }
+        const bool luma_row = (y == 2 * cj) || (y == 2 * cj + 1);
+        __align__(8) unsigned char ly[2 * VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const int r0 = px[(2 * v) * IPP], g0 = px[(2 * v) * IPP + 1], b0 = px[(2 * v) * IPP + 2];
+            const int r1 = px[(2 * v + 1) * IPP], g1 = px[(2 * v + 1) * IPP + 1], b1 = px[(2 * v + 1) * IPP + 2];
+            ly[2 * v] = ncr_clip8((((((8414 * r0 + 16519 * g0 + 3208 * b0 + (32 << 14) + (1 << 8)) >> 9) << 1) + 64) >> 7));
+            ly[2 * v + 1] = ncr_clip8((((((8414 * r1 + 16519 * g1 + 3208 * b1 + (32 << 14) + (1 << 8)) >> 9) << 1) + 64) >> 7));
+            const int r2 = r0 + r1, g2 = g0 + g1, b2 = b0 + b1;
+            const int u15 = min(((-4865 * r2 - 9528 * g2 + 14392 * b2 + (0x4001 << 9)) >> 10) << 1, 32767);
+            const int v15 = min(((14392 * r2 - 12061 * g2 - 2332 * b2 + (0x4001 << 9)) >> 10) << 1, 32767);
+            if (last) { au[v] += u15 * coef[k]; av[v] += v15 * coef[k]; }
+            else { au[v] += (u15 * coef[k]) >> 16; av[v] += (v15 * coef[k]) >> 16; }
+        }
+        if (luma_row) {
+            if (VEC == 4) {
+                *(uint2*)(Y + (size_t)y * w + 8 * bx) = *(const uint2*)ly;
+            } else {
+                Y[(size_t)y * w + 2 * bx] = ly[0];
+                if (2 * bx + 1 < w) Y[(size_t)y * w + 2 * bx + 1] = ly[1];
+            }
         }
     }
-    const int r = (sr + 2) >> 2, g = (sg + 2) >> 2, b = (sb + 2) >> 2;
-    U[(size_t)by * cw + bx] = (unsigned char)(((-38 * r - 74 * g + 112 * b + 128) >> 8) + 128);
-    V[(size_t)by * cw + bx] = (unsigned char)(((112 * r - 94 * g - 18 * b + 128) >> 8) + 128);
+    __align__(4) unsigned char lu[VEC], lv[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        lu[v] = ncr_clip8(last ? (au[v] >> 19) : (au[v] >> 3));
+        lv[v] = ncr_clip8(last ? (av[v] >> 19) : (av[v] >> 3));
+    }
+    if (VEC == 4) {
+        *(uint32_t*)(U + (size_t)cj * cw + 4 * bx) = *(const uint32_t*)lu;
+        *(uint32_t*)(V + (size_t)cj * cw + 4 * bx) = *(const uint32_t*)lv;
+    } else {
+        U[(size_t)cj * cw + bx] = lu[0];
+        V[(size_t)cj * cw + bx] = lv[0];
+    }
 }
 
 // ResampleTexture, reference cpp:950-976: out(i,j) = nearest(in, (f64)i / width * in.w, (f64)j / height * in.h).
@@ -290,7 +359,9 @@ extern "C" void ncr_launch_flush(const NcrFlushArgs* A, cudaStream_t s, cudaEven
     const int n_bins = A->d.bins_x * A->d.bins_y;
     cudaMemsetAsync(A->cursors, 0, 8 * sizeof(uint32_t), s);
     if (ev) cudaEventRecord(ev[0], s);
-    if (A->n_cmds) {
+    if (A->coarse_list == nullptr) {
+        // small batch: no coarse pass (one kernel and one dependency less per flush)
+    } else if (A->n_cmds) {
         // hit masks of the counting scan: one bit per command per CTA, rounded up to whole 128-command steps per warp
         const uint32_t seg = ((A->n_cmds + NCR_COARSE_WARPS - 1) / NCR_COARSE_WARPS + 31) & ~31u;
         const uint32_t mask_words = (seg + 32 * NCR_COARSE_U - 1) / (32 * NCR_COARSE_U) * NCR_COARSE_U;
@@ -304,6 +375,7 @@ extern "C" void ncr_launch_flush(const NcrFlushArgs* A, cudaStream_t s, cudaEven
     ncr_bin_fine<<<(n_tiles + 7) / 8, 256, 0, s>>>(*A);
     if (ev) cudaEventRecord(ev[2], s);
     ncr_launch_composite(A, s);
+    if (A->yuv_out && A->u8_out) ncr_launch_yuv420p(A->u8_out, A->yuv_out, A->d.w, A->d.h, A->d.ipp, s);   // present path
     if (ev) cudaEventRecord(ev[3], s);
 }
 
@@ -314,57 +386,19 @@ extern "C" void ncr_launch_convert_u8(const double* fb, unsigned char* out, size
     ncr_convert_u8<<<blocks, 256, 0, s>>>(fb, out, n);
 }
 
-// Same conversion for widths that are a multiple of 8 (1080p, 4K): one thread per 8x2 pixel block, 64-bit / 128-bit loads
-// of the image rows, one 8-byte store per luma row and one 4-byte store per chroma plane.
-template <int IPP>
-__global__ void __launch_bounds__(256) ncr_yuv420p_w8(const unsigned char* __restrict__ img, unsigned char* __restrict__ out,
-                                                      int w, int h) {
-    const int ch = (h + 1) >> 1, cw = w >> 1, w8 = w >> 3;
-    const int bx = blockIdx.x * 32 + (threadIdx.x & 31), by = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (bx >= w8 || by >= ch) return;
-    unsigned char* Y = out;
-    unsigned char* U = out + (size_t)w * h;
-    unsigned char* V = U + (size_t)cw * ch;
-    int sr[4] = {0, 0, 0, 0}, sg[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int dy = 0; dy < 2; ++dy) {
-        const int yr = 2 * by + dy, y = min(yr, h - 1);
-        unsigned char px[8 * IPP];
-        const unsigned char* row = img + ((size_t)y * w + 8 * bx) * IPP;   // 8*IPP bytes, 8-byte aligned because w % 8 == 0
-#pragma unroll
-        for (int k = 0; k < IPP; ++k) ((uint2*)px)[k] = __ldg((const uint2*)row + k);
-        unsigned char ly[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = px[i * IPP], g = px[i * IPP + 1], b = px[i * IPP + 2];
-            sr[i >> 1] += r; sg[i >> 1] += g; sb[i >> 1] += b;
-            ly[i] = (unsigned char)(((66 * r + 129 * g + 25 * b + 128) >> 8) + 16);
-        }
-        if (yr < h) *(uint2*)(Y + (size_t)y * w + 8 * bx) = *(const uint2*)ly;
-    }
-    unsigned char lu[4], lv[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int r = (sr[k] + 2) >> 2, g = (sg[k] + 2) >> 2, b = (sb[k] + 2) >> 2;
-        lu[k] = (unsigned char)(((-38 * r - 74 * g + 112 * b + 128) >> 8) + 128);
-        lv[k] = (unsigned char)(((112 * r - 94 * g - 18 * b + 128) >> 8) + 128);
-    }
-    *(uint32_t*)(U + (size_t)by * cw + 4 * bx) = *(const uint32_t*)lu;
-    *(uint32_t*)(V + (size_t)by * cw + 4 * bx) = *(const uint32_t*)lv;
-}
-
 extern "C" void ncr_launch_yuv420p(const unsigned char* img, unsigned char* out, int w, int h, int ipp, cudaStream_t s) {
     if (w <= 0 || h <= 0) return;
+    const int cw = (w + 1) / 2, ch = (h + 1) / 2;
     // the vector variant needs every row, the luma plane and both chroma planes to start on the alignment of its accesses
-    if (w % 8 == 0 && (((size_t)w * h) % 8 == 0) && ((((size_t)w / 2) * ((h + 1) / 2)) % 4 == 0)) {
-        dim3 grid((w / 8 + 31) / 32, ((h + 1) / 2 + 7) / 8);
-        if (ipp == 4) ncr_yuv420p_w8<4><<<grid, 256, 0, s>>>(img, out, w, h);
-        else ncr_yuv420p_w8<3><<<grid, 256, 0, s>>>(img, out, w, h);
+    if (w % 8 == 0 && (((size_t)w * h) % 8 == 0) && (((size_t)cw * ch) % 4 == 0)) {
+        dim3 grid((cw / 4 + 31) / 32, (ch + 7) / 8);
+        if (ipp == 4) ncr_yuv420p<4, 4><<<grid, 256, 0, s>>>(img, out, w, h);
+        else ncr_yuv420p<3, 4><<<grid, 256, 0, s>>>(img, out, w, h);
         return;
     }
-    dim3 grid(((w + 1) / 2 + 31) / 32, ((h + 1) / 2 + 7) / 8);
-    if (ipp == 4) ncr_yuv420p<4><<<grid, 256, 0, s>>>(img, out, w, h);
-    else ncr_yuv420p<3><<<grid, 256, 0, s>>>(img, out, w, h);
+    dim3 grid((cw + 31) / 32, (ch + 7) / 8);
+    if (ipp == 4) ncr_yuv420p<4, 1><<<grid, 256, 0, s>>>(img, out, w, h);
+    else ncr_yuv420p<3, 1><<<grid, 256, 0, s>>>(img, out, w, h);
 }
 
 extern "C" void ncr_launch_resample(const NcrCmd* src, void* out, int ow, int oh, cudaStream_t s) {

@@ -84,22 +84,29 @@ struct NcrFlushArgs {
     NcrFrameDims d;
     double* fb;                 // canonical f64 canvas [h][w][ipp]
     unsigned char* u8_out;      // fused (iu8)(v*255) image, or nullptr
-    unsigned char* yuv_out;     // fused YUV 4:2:0 planes of that image (present path), or nullptr
+    unsigned char* yuv_out;     // YUV 4:2:0 planes of that image (present path; ncr_yuv420p runs right after the composite), or nullptr
     const NcrCmd* cmds;
     const NcrBox* boxes;
     const uint32_t* binboxes;   // per command: first/last 128-px bin touched per axis, 4 x u8 (x0 x1 y0 y1), or nullptr
     const double* aux;
     uint32_t n_cmds;
     uint32_t load_fb;           // 0: every tile's list starts with SET_COLOR, do not read fb
-    uint32_t* coarse_list;      // capacity coarse_cap
+    uint32_t* coarse_list;      // capacity coarse_cap; nullptr: small batch — ncr_bin_coarse is skipped and ncr_bin_fine scans the commands directly
     uint32_t* coarse_off;       // [bins] offset, [bins] count
     uint32_t* fine_list;        // capacity fine_cap; entries: command index | NCR_ENTRY_INTERIOR
     uint32_t* fine_off;         // per region: {offset, count} (uint2[regions])
     uint32_t* cursors;          // [0] coarse cursor, [1] fine cursor, [2..3] blended-pixel counter (u64), [4] overflow flag,
-                                // [5] composite work counter (regions handed out)
+                                // [5] composite work counter (regions handed out), [6] list entries tagged interior (statistics)
     uint32_t coarse_cap, fine_cap;
     uint32_t count_pixels;      // stats mode: count APPLY executions
     uint32_t write_fb;          // 0: present-only flush — the f64 canvas is NOT written back (the host marks it stale and
                                 // re-runs this batch with write_fb = 1 if anyone ever reads it; see api.cu materialize())
     uint32_t prefetch;          // composite variant: 1 = next region's header / list / first command fetched during the current one
+    // Experiment X5 (profiles/README.md; only read by kernels built with NCR_TMA_IDENT, only filled when NCR_TMA=1): the batch's
+    // first full-resolution identity-path DrawTexture of an RGBA8 texture at integer (x, y) — milrenderer's background — whose
+    // 16x8 texel box per region can be staged by the TMA unit one region ahead.
+    const void* tma_map;        // CUtensorMap of the texture (device memory), or nullptr
+    int32_t tma_cmd;            // index of that command in cmds
+    int32_t tma_x, tma_y;       // its integer destination origin
+    int32_t tma_w, tma_h;       // texture size in texels
 };

@@ -205,8 +205,11 @@ double ncr_replay_run(void* api, void* ctx, const void* trace, long bytes, void*
 // n_threads workers, each with its own context of the given shape, each replaying the trace `repeats` times.
 // warm_repeats untimed passes come first.  Returns wall seconds of the timed passes until the last worker finishes
 // (contexts are created before the clock starts).
-double ncr_replay_run_threads(void* api, int n_threads, long width, long height, int alpha, const void* trace, long bytes,
-                              void* const* textures, long n_textures, int repeats, int warm_repeats) {
+// frames_out (may be null): n_threads consecutive buffers of frame_stride bytes; receives each worker's LAST frame after the
+// clock has stopped, so that the caller can check what the timed passes rendered.
+double ncr_replay_run_threads_ex(void* api, int n_threads, long width, long height, int alpha, const void* trace, long bytes,
+                                 void* const* textures, long n_textures, int repeats, int warm_repeats, unsigned char* frames_out,
+                                 long frame_stride) {
     const Api& a = *(const Api*)api;
     std::vector<H> ctxs(n_threads);
     std::vector<std::vector<unsigned char>> pageable(n_threads);
@@ -238,12 +241,23 @@ double ncr_replay_run_threads(void* api, int n_threads, long width, long height,
     const auto t1 = std::chrono::steady_clock::now();
     bool bad = false;
     for (int k = 0; k < n_threads; ++k) {
+        if (frames_out) {
+            long n = a.present_mode == 1 ? frame_stride : (long)a.GetBufferSize(ctxs[k]);
+            if (n > frame_stride) n = frame_stride;
+            memcpy(frames_out + (size_t)k * frame_stride, frames[k], (size_t)n);
+        }
         a.DestroyRenderContext(ctxs[k]);
         if (pinned && pageable[k].empty()) a.NcrFreeHost(frames[k]);
         if (rc[k] < 0) bad = true;
     }
     if (bad) return -1.0;
     return std::chrono::duration<double>(t1 - t0).count();
+}
+
+double ncr_replay_run_threads(void* api, int n_threads, long width, long height, int alpha, const void* trace, long bytes,
+                              void* const* textures, long n_textures, int repeats, int warm_repeats) {
+    return ncr_replay_run_threads_ex(api, n_threads, width, height, alpha, trace, bytes, textures, n_textures, repeats,
+                                     warm_repeats, nullptr, 0);
 }
 
 }   // extern "C"

@@ -146,6 +146,8 @@ class Replayer:
         self.lib.ncr_replay_run_threads.restype = ctypes.c_double
         self.lib.ncr_replay_run_threads.argtypes = (ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_int,
                                                     ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_int)
+        self.lib.ncr_replay_run_threads_ex.restype = ctypes.c_double
+        self.lib.ncr_replay_run_threads_ex.argtypes = self.lib.ncr_replay_run_threads.argtypes + (ctypes.c_void_p, ctypes.c_long)
         self.lib.ncr_replay_set_present.restype = ctypes.c_int
         self.lib.ncr_replay_set_present.argtypes = (ctypes.c_void_p, ctypes.c_int)
         self.api = self.lib.ncr_replay_open(target_lib_path.encode())
@@ -166,11 +168,13 @@ class Replayer:
         return secs
 
     def run_threads(self, n_threads: int, width: int, height: int, alpha: bool, trace: np.ndarray, textures,
-                    repeats: int = 1, warm_repeats: int = 0) -> float:
+                    repeats: int = 1, warm_repeats: int = 0, frames_out: np.ndarray | None = None) -> float:
+        """``frames_out``: uint8 array of shape (n_threads, frame_bytes) that receives every worker's last frame (after the clock stops)."""
         table = texture_table(textures)
-        secs = self.lib.ncr_replay_run_threads(self.api, n_threads, width, height, int(alpha),
-                                               ctypes.c_void_p(trace.ctypes.data), trace.nbytes, table, len(textures), repeats,
-                                               warm_repeats)
+        out_p, stride = (ctypes.c_void_p(frames_out.ctypes.data), frames_out.shape[1]) if frames_out is not None else (None, 0)
+        secs = self.lib.ncr_replay_run_threads_ex(self.api, n_threads, width, height, int(alpha),
+                                                  ctypes.c_void_p(trace.ctypes.data), trace.nbytes, table, len(textures), repeats,
+                                                  warm_repeats, out_p, stride)
         if secs < 0:
             raise ValueError("replay failed")
         return secs

@@ -197,11 +197,13 @@ static void raster(Canvas* c, Box bx, const Shader* s) {
     for (i64 j = bx.t; j < bx.b; ++j) {
         for (i64 i = bx.l; i < bx.r; ++i) {
             f64 X, Y, rgba[4];
-            if (s->kind == K_PERSP) {   /* extension: X = (h0*i + h1*j + h2) / (h6*i + h7*j + h8), likewise Y */
+            if (s->kind == K_PERSP) {   /* extension (this repo's own spec, parity unpinned): rw = 1 / (h6*i + h7*j + h8);
+                                         * X = (h0*i + h1*j + h2) * rw, Y = (h3*i + h4*j + h5) * rw — one division per pixel */
                 f64 fi = (f64)i, fj = (f64)j;
                 f64 hw = s->hom[0] * fi + s->hom[1] * fj + s->hom[2];
-                X = (s->inv[0] * fi + s->inv[1] * fj + s->inv[2]) / hw;
-                Y = (s->inv[3] * fi + s->inv[4] * fj + s->inv[5]) / hw;
+                f64 rw = 1.0 / hw;
+                X = (s->inv[0] * fi + s->inv[1] * fj + s->inv[2]) * rw;
+                Y = (s->inv[3] * fi + s->inv[4] * fj + s->inv[5]) * rw;
                 if (!(hw > 0.0)) continue;
             } else {
                 map_point(s->inv, (f64)i, (f64)j, &X, &Y);
@@ -573,16 +575,27 @@ void NcrDrawTexturePerspective(Canvas* c, Image* tex, const f64* hinv, f64 x, f6
     release_operand(t);
 }
 
-/* ---------------------------------------------------------------- present path — PARITY UNPINNED
- * PutRendererContextFrame (cpp:232-256) truncates the canvas to u8 and hands it to libswscale for RGB(A) -> YUV420P.
- * libswscale (FFmpeg, un-vendored third-party dependency; the reference pins no version) is absent here, so its exact
- * rounding cannot be reproduced or checked.  This restates the published BT.601 studio-swing 8-bit integer matrix
- *   Y = ((66R + 129G + 25B + 128) >> 8) + 16,  U = ((-38R - 74G + 112B + 128) >> 8) + 128,
- *   V = ((112R - 94G - 18B + 128) >> 8) + 128
- * (known answers: black 16/128/128, white 235/128/128, red 82/90/240, green 144/54/34, blue 41/240/110), with chroma
- * from the rounded mean of each 2x2 block and edge replication for odd sizes.  It only checks the product against this
- * repo's own definition. */
-static int floor_shift8(int v) { return (v >= 0) ? (v >> 8) : -((-v + 255) >> 8); }   /* floor(v / 256) without relying on signed >> */
+/* ---------------------------------------------------------------- present path
+ * PutRendererContextFrame (cpp:232-256) truncates the canvas to u8 and hands it to libswscale:
+ *     sws_getContext(w, h, RGBA | RGB24, w, h, YUV420P, SWS_BILINEAR, 0, 0, 0);  sws_scale(...)          (cap size == canvas size)
+ * libswscale is an un-vendored third-party dependency of the reference (FFmpeg; the reference pins no version).  This is a
+ * restatement of what libswscale computes on x86-64 for exactly that call — its published algorithm (libswscale/input.c
+ * rgb24ToY_c / rgb24ToUV_half_c and their rgb32 twins, utils.c initFilter, x86/yuv2yuvX.asm, swscale.c) with the BT.601
+ * limited-range table — PINNED against a real build: libswscale 9.1.100 (FFmpeg 8), the copy bundled with this image's
+ * opencv-python-headless wheel, driven through ctypes by tests/golden/make_swscale_fixtures.py; bit-exact Y, U and V for
+ * RGBA and RGB24 input on every even size >= 8x8 tried (tests/test_oracle.py).  Odd sizes and heights below 8 follow the same
+ * formulas with clamped neighbours — this repo's own definition, not pinned.
+ *
+ *   luma    Y14 = (8414 R + 16519 G + 3208 B + (32 << 14) + (1 << 8)) >> 9;  Y15 = Y14 << 1;  Y = clip8((Y15 + 64) >> 7)
+ *   chroma  horizontal: the SUM of each pixel pair (R2 = R[2i] + R[2i+1], ...):
+ *               U14 = (-4865 R2 - 9528 G2 + 14392 B2 + (0x4001 << 9)) >> 10,  V14 = (14392 R2 - 12061 G2 - 2332 B2 + (0x4001 << 9)) >> 10
+ *               U15 = min(U14 << 1, 32767)
+ *           vertical: bilinear 2:1 = taps {512, 1536, 1536, 512} / 4096 on rows 2c-1 .. 2c+2, taps that fall outside the
+ *               image folded onto the edge row (initFilter).  Without SWS_ACCURATE_RND — the reference sets no flag — x86
+ *               runs the 16-bit vertical scaler: acc = ((64 + 8 * 3) >> 4) + sum_k ((U15[k] * coeff[k]) >> 16), U = clip8(acc >> 3)
+ *               (pmulhw per tap; the bias term compensates its truncation); the LAST chroma row is produced by the C
+ *               scaler (swscale.c switches for dstY >= dstH - 2): U = clip8(((64 << 12) + sum_k U15[k] * coeff[k]) >> 19). */
+static u8 clip8(i64 v) { return (u8)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
 long NcrYUV420PSize(Canvas* c) {
     if (c->w <= 0 || c->h <= 0) return 0;
     return (long)(c->w * c->h + 2 * ((c->w + 1) / 2) * ((c->h + 1) / 2));
@@ -592,29 +605,54 @@ long NcrGetBufferAsYUV420P(Canvas* c, u8* out) {
     const int ipp = c->ipp;
     if (w <= 0 || h <= 0) return 0;
     u8* img = (u8*)malloc((size_t)(w * h * ipp));
-    if (!img) return -1;
+    int* u15 = (int*)malloc((size_t)(h * cw) * sizeof(int));
+    int* v15 = (int*)malloc((size_t)(h * cw) * sizeof(int));
+    if (!img || !u15 || !v15) { free(img); free(u15); free(v15); return -1; }
     GetBufferAsUInt8(c, img);
     u8 *Y = out, *U = out + w * h, *V = U + cw * ch;
-    for (i64 j = 0; j < h; ++j)
+    for (i64 j = 0; j < h; ++j) {
         for (i64 i = 0; i < w; ++i) {
             const u8* q = img + (j * w + i) * ipp;
-            Y[j * w + i] = (u8)(floor_shift8(66 * q[0] + 129 * q[1] + 25 * q[2] + 128) + 16);
+            const i64 y14 = (8414 * (i64)q[0] + 16519 * (i64)q[1] + 3208 * (i64)q[2] + (32 << 14) + (1 << 8)) >> 9;
+            Y[j * w + i] = clip8(((y14 << 1) + 64) >> 7);
         }
-    for (i64 bj = 0; bj < ch; ++bj)
-        for (i64 bi = 0; bi < cw; ++bi) {
-            int sum[3] = {0, 0, 0};
-            for (int dy = 0; dy < 2; ++dy)
-                for (int dx = 0; dx < 2; ++dx) {
-                    i64 x = 2 * bi + dx, y = 2 * bj + dy;
-                    if (x > w - 1) x = w - 1;
-                    if (y > h - 1) y = h - 1;
-                    const u8* q = img + (y * w + x) * ipp;
-                    for (int k = 0; k < 3; ++k) sum[k] += q[k];
-                }
-            const int r = (sum[0] + 2) / 4, g = (sum[1] + 2) / 4, b = (sum[2] + 2) / 4;
-            U[bj * cw + bi] = (u8)(floor_shift8(-38 * r - 74 * g + 112 * b + 128) + 128);
-            V[bj * cw + bi] = (u8)(floor_shift8(112 * r - 94 * g - 18 * b + 128) + 128);
+        for (i64 i = 0; i < cw; ++i) {
+            const i64 x0 = 2 * i, x1 = (2 * i + 1 < w) ? 2 * i + 1 : w - 1;
+            const u8 *p0 = img + (j * w + x0) * ipp, *p1 = img + (j * w + x1) * ipp;
+            const i64 r2 = p0[0] + p1[0], g2 = p0[1] + p1[1], b2 = p0[2] + p1[2];
+            i64 u = ((-4865 * r2 - 9528 * g2 + 14392 * b2 + ((i64)0x4001 << 9)) >> 10) << 1;
+            i64 v = ((14392 * r2 - 12061 * g2 - 2332 * b2 + ((i64)0x4001 << 9)) >> 10) << 1;
+            u15[j * cw + i] = (int)(u > 32767 ? 32767 : u);
+            v15[j * cw + i] = (int)(v > 32767 ? 32767 : v);
         }
-    free(img);
+    }
+    static const int taps[4] = {512, 1536, 1536, 512};
+    for (i64 cj = 0; cj < ch; ++cj) {
+        /* rows 2cj-1 .. 2cj+2, out-of-image taps folded onto the edge row: at most 4 distinct rows */
+        i64 row[4]; int coef[4]; int n = 0;
+        for (int k = 0; k < 4; ++k) {
+            i64 y = 2 * cj - 1 + k;
+            if (y < 0) y = 0;
+            if (y > h - 1) y = h - 1;
+            if (n && row[n - 1] == y) coef[n - 1] += taps[k];
+            else { row[n] = y; coef[n] = taps[k]; ++n; }
+        }
+        const int last = (cj == ch - 1);
+        for (i64 i = 0; i < cw; ++i) {
+            i64 au, av;
+            if (last) {
+                au = av = (i64)64 << 12;
+                for (int k = 0; k < n; ++k) { au += (i64)u15[row[k] * cw + i] * coef[k]; av += (i64)v15[row[k] * cw + i] * coef[k]; }
+                au >>= 19; av >>= 19;
+            } else {
+                au = av = (64 + 8 * 3) >> 4;
+                for (int k = 0; k < n; ++k) { au += ((i64)u15[row[k] * cw + i] * coef[k]) >> 16; av += ((i64)v15[row[k] * cw + i] * coef[k]) >> 16; }
+                au >>= 3; av >>= 3;
+            }
+            U[cj * cw + i] = clip8(au);
+            V[cj * cw + i] = clip8(av);
+        }
+    }
+    free(img); free(u15); free(v15);
     return NcrYUV420PSize(c);
 }

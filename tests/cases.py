@@ -19,6 +19,66 @@ def digest(ctx) -> dict:
     return {"u8": sha(ctx.get_buffer_as_uint8()), "f64": sha(ctx.get_buffer_np().tobytes())}
 
 
+def swscale_fixtures():
+    """Inputs and outputs of a real libswscale for the present path's conversion (tests/golden/make_swscale_fixtures.py)."""
+    import os
+
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "swscale_fixtures.npz"))
+
+
+def swscale_model(img):
+    """numpy restatement of libswscale's RGB(A) -> YUV420P conversion for even sizes (the formulas of oracle/ncr_oracle.c,
+    vectorised; validated against the real library by tests/test_oracle.py).  Returns the concatenated Y, U, V planes."""
+    h, w, _ = img.shape
+    assert h % 2 == 0 and w % 2 == 0 and h >= 4
+    r, g, b = (img[..., k].astype(np.int64) for k in range(3))
+    y = np.clip((((8414 * r + 16519 * g + 3208 * b + (32 << 14) + (1 << 8)) >> 9 << 1) + 64) >> 7, 0, 255)
+    r2, g2, b2 = (c[:, 0::2] + c[:, 1::2] for c in (r, g, b))
+    u15 = np.minimum(((-4865 * r2 - 9528 * g2 + 14392 * b2 + (0x4001 << 9)) >> 10) << 1, 32767)
+    v15 = np.minimum(((14392 * r2 - 12061 * g2 - 2332 * b2 + (0x4001 << 9)) >> 10) << 1, 32767)
+
+    def vertical(p):
+        ch = h // 2
+        out = np.zeros((ch, w // 2), dtype=np.int64)
+        for c in range(ch):
+            taps = {}
+            for k, cf in zip(range(2 * c - 1, 2 * c + 3), (512, 1536, 1536, 512)):
+                kk = min(max(k, 0), h - 1)
+                taps[kk] = taps.get(kk, 0) + cf
+            if c == ch - 1:
+                out[c] = ((64 << 12) + sum(p[kk] * cf for kk, cf in taps.items())) >> 19
+            else:
+                out[c] = (5 + sum((p[kk] * cf) >> 16 for kk, cf in taps.items())) >> 3
+        return np.clip(out, 0, 255)
+
+    return np.concatenate([a.astype(np.uint8).ravel() for a in (y, vertical(u15), vertical(v15))])
+
+
+def canvas_holding_u8_image(R, img):
+    """A context whose GetBufferAsUInt8 readback is exactly ``img`` (h, w, 3|4 uint8), built through the reference ABI: an f64
+    texture with texels (k + 0.5) / 255 — (iu8)(v * 255) truncates to k for every k — drawn 1:1 on the identity path.  The
+    texture is one texel larger than the canvas because the last texel row / column is never sampled."""
+    h, w, c = img.shape
+    tex = np.zeros((h + 1, w + 1, 4), dtype=np.float64)
+    tex[:h, :w, :c] = (img.astype(np.float64) + 0.5) / 255.0
+    if c == 3:
+        tex[..., 3] = 1.0     # a == 1: the source colour is stored untouched (cpp:533)
+    else:
+        # RGBA canvas: alpha is both the stored alpha and the blend factor; blend over a black canvas would scale rgb, so the
+        # image's alpha plane is injected with set_pixel afterwards
+        tex[..., 3] = 1.0
+    ctx = R.RenderContext(w, h, c == 4)
+    ctx.set_color(0, 0, 0, 0)
+    t = R.Texture(w + 1, h + 1, True, tex.tobytes(), is_uint8=False)
+    ctx.draw_texture(t, 0, 0, w + 1, h + 1)
+    if c == 4:
+        for (j, i), a in np.ndenumerate(img[..., 3]):
+            if a != 255:
+                px = (img[j, i].astype(np.float64) + 0.5) / 255.0
+                ctx.set_pixel(int(i), int(j), *px)
+    return ctx
+
+
 def tiny_textures(R, image_rgba):
     rs = np.random.RandomState(99)
     return [

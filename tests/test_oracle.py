@@ -82,10 +82,46 @@ def test_u8_truncation_edge_values(port, ref):
     assert got[0] == got[1] == [254, 254, 0, 44, 0, 0, 255, 254, 159, 85, 0, 0]
 
 
-def test_yuv420p_restatement_known_answers(port):
-    """Present path, PARITY UNPINNED against libswscale (absent): the restatement reproduces the published
-    BT.601 studio-swing known answers for the primaries, on RGB and RGBA canvases, with odd sizes (edge replication)."""
-    kat = {(0, 0, 0): (16, 128, 128), (1, 1, 1): (235, 128, 128), (1, 0, 0): (82, 90, 240), (0, 1, 0): (144, 54, 34),
+def test_yuv420p_restatement_reproduces_libswscale_fixtures(port):
+    """Present path, pinned: for the call PutRendererContextFrame makes (cpp:241-256), the restatement's Y, U, V
+    planes are byte-identical to a real libswscale's (fixtures: libswscale 9.1.100, tests/golden/make_swscale_fixtures.py) —
+    RGBA and RGB24 canvases, noise, saturated primaries, ramps, widths that are not multiples of 16."""
+    fx = cases.swscale_fixtures()
+    assert list(fx["version"]) == [9, 1, 100]
+    k = 0
+    while f"img_{k}" in fx:
+        img = fx[f"img_{k}"]
+        ctx = cases.canvas_holding_u8_image(port, img)
+        assert bytes(ctx.get_buffer_as_uint8()) == img.tobytes()
+        assert ctx.get_buffer_as_yuv420p().tobytes() == fx[f"yuv_{k}"].tobytes(), f"fixture {k} {img.shape}"
+        k += 1
+    assert k >= 5
+
+
+def test_yuv420p_restatement_matches_a_live_libswscale(port):
+    """The same against whatever libswscale this machine has (the opencv wheel bundles one), on fresh random images at video
+    sizes; skipped where none can be loaded."""
+    import sys
+
+    from conftest import GOLDEN_DIR
+
+    sys.path.insert(0, GOLDEN_DIR)
+    import make_swscale_fixtures as mk
+
+    libs = mk.load_swscale()
+    if libs is None:
+        pytest.skip("no libswscale on this machine")
+    rs = np.random.RandomState(77)
+    for shape in ((180, 320, 3), (90, 160, 4), (8, 8, 3), (24, 40, 4)):
+        img = rs.randint(0, 256, shape).astype(np.uint8)
+        ctx = cases.canvas_holding_u8_image(port, img)
+        assert ctx.get_buffer_as_yuv420p().tobytes() == mk.swscale_yuv420p(libs, img).tobytes(), shape
+
+
+def test_yuv420p_known_answers_and_odd_sizes(port):
+    """BT.601 limited-range known answers as libswscale rounds them (red is 81, not the 82 of the 8-bit-shift matrix), on RGB
+    and RGBA canvases with odd sizes (clamped neighbours: this repo's definition there, not pinned)."""
+    kat = {(0, 0, 0): (16, 128, 128), (1, 1, 1): (235, 128, 128), (1, 0, 0): (81, 90, 240), (0, 1, 0): (145, 54, 34),
            (0, 0, 1): (41, 240, 110)}
     for alpha in (True, False):
         for (r, g, b), (y, u, v) in kat.items():
@@ -95,11 +131,3 @@ def test_yuv420p_restatement_known_answers(port):
             out = ctx.get_buffer_as_yuv420p()
             assert out.size == 5 * 3 + 2 * 3 * 2
             assert set(out[:15]) == {y} and set(out[15:21]) == {u} and set(out[21:]) == {v}
-    # chroma is the rounded 2x2 mean, luma is per pixel
-    ctx = port.RenderContext(2, 2, True)
-    ctx.set_color(0, 0, 0, 1)
-    ctx.set_pixel(0, 0, 1, 0, 0, 1)
-    out = ctx.get_buffer_as_yuv420p()
-    assert list(out[:4]) == [82, 16, 16, 16]
-    r = (255 + 2) // 4
-    assert out[4] == ((-38 * r + 128) >> 8) + 128 and out[5] == ((112 * r + 128) >> 8) + 128

@@ -408,17 +408,17 @@ def test_perspective_pixel_box_is_conservative(gpu, port):
 
 
 @pytest.mark.parametrize("shape", [(160, 90, True), (160, 90, False), (97, 61, False), (257, 129, True), (2, 2, False), (1, 1, True), (8, 3, True), (24, 5, False)])
-def test_yuv420p_present_matches_port_parity_unpinned(shape, gpu, port, image_rgba):
+def test_yuv420p_present_matches_port(shape, gpu, port, image_rgba):
     """Present path: NcrGetBufferAsYUV420P (flush + fused u8 image + ncr_yuv420p + 1.5 B/px readback) against
-    the C restatement on the same random stream.  PARITY UNPINNED w.r.t. libswscale (third-party, absent); the u8 image
-    the planes are computed from IS pinned (it is GetBufferAsUInt8's)."""
+    the C restatement on the same random stream, incl. odd and tiny sizes (those follow this repo's clamped-neighbour
+    definition; even sizes >= 8x8 are pinned to libswscale, see test_present_path_reproduces_libswscale)."""
     w, h, alpha = shape
     got = []
     for R in (gpu, port):
         ctx = R.RenderContext(w, h, alpha)
         tex = cases.tiny_textures(R, image_rgba)
         streams.stream_random(ctx, tex, 77, n=60)
-        yuv = ctx.get_buffer_as_yuv420p()          # draws pending: planes come fused out of the composite
+        yuv = ctx.get_buffer_as_yuv420p()          # draws pending: composite (u8 image) + ncr_yuv420p in one flush
         assert yuv.size == w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2)
         again = ctx.get_buffer_as_yuv420p()        # nothing pending, planes still current: just a copy
         ctx.fill_color(.3, .6, .9, .25)
@@ -443,14 +443,18 @@ def test_yuv420p_full_size_and_video_cap_path(gpu):
     streams.stream_c4_frame(rec, slots[0], slots[1:], frame=7, n_notes=300)
     trace.submit_trace(ctx, rec.as_array(), tex)
     yuv = ctx.get_buffer_as_yuv420p()
-    img = np.frombuffer(ctx.get_buffer_as_uint8(), dtype=np.uint8).reshape(h, w, 3).astype(np.int32)
-    y = ((66 * img[..., 0] + 129 * img[..., 1] + 25 * img[..., 2] + 128) >> 8) + 16
-    assert np.array_equal(yuv[: w * h].reshape(h, w), y.astype(np.uint8))
-    m = (img.reshape(h // 2, 2, w // 2, 2, 3).sum(axis=(1, 3)) + 2) >> 2
-    u = ((-38 * m[..., 0] - 74 * m[..., 1] + 112 * m[..., 2] + 128) >> 8) + 128
-    v = ((112 * m[..., 0] - 94 * m[..., 1] - 18 * m[..., 2] + 128) >> 8) + 128
-    assert np.array_equal(yuv[w * h: w * h + w * h // 4].reshape(h // 2, w // 2), u.astype(np.uint8))
-    assert np.array_equal(yuv[w * h + w * h // 4:].reshape(h // 2, w // 2), v.astype(np.uint8))
+    img = np.frombuffer(ctx.get_buffer_as_uint8(), dtype=np.uint8).reshape(h, w, 3)
+    assert np.array_equal(yuv, cases.swscale_model(img))       # libswscale's arithmetic (pinned: tests/test_oracle.py)
+    import sys
+
+    from conftest import GOLDEN_DIR
+
+    sys.path.insert(0, GOLDEN_DIR)
+    import make_swscale_fixtures as mk
+
+    libs = mk.load_swscale()
+    if libs is not None:                                        # and the real library, where this machine has one
+        assert yuv.tobytes() == mk.swscale_yuv420p(libs, img).tobytes()
     raw = ctypes.CDLL(gpu.path)   # the video entry points are not part of the render binding: plain ctypes, as pyb:425-478 does
     raw.CreateVideoCap.restype = ctypes.c_void_p
     raw.CreateVideoCap.argtypes = (ctypes.c_long, ctypes.c_long, ctypes.c_double)
@@ -696,7 +700,7 @@ def test_video_frames_never_write_the_canvas_back(gpu, image_rgba):
     st = ctx.stats()
     assert st.materialized == before.materialized == 0
     assert st.flushes - before.flushes == 6
-    assert st.kernel_launches - before.kernel_launches == 18   # bin_coarse + bin_fine + composite per frame
+    assert st.kernel_launches - before.kernel_launches == 12   # bin_fine + composite per frame (31 commands: no coarse pass)
 
 
 def test_u8_truncation_edge_values_on_the_gpu(gpu, port):
@@ -732,3 +736,120 @@ def test_u8_truncation_edge_values_on_the_gpu(gpu, port):
         outs.append(out)
     assert outs[0][0] == [254, 254, 0, 44, 0, 0, 255, 254, 159, 85, 0, 0]
     assert outs[0] == outs[1]
+
+
+def test_contexts_on_explicit_devices_and_multi_device_frame_pool(gpu, image_rgba):
+    """One host process, several GPUs (what milrenderer.py needs on an 8-GPU box): contexts are placed on explicit devices,
+    a texture created once is copied to a device the first time a context there draws it, and a frame pool spread over
+    the devices delivers the same frames, in order, as a single-device pool.  With one visible device the pool is spread
+    over [0, 0]; with two or more (gpurun --gpus 2) the second device really renders."""
+    from libnativecpurenderer_b200 import batch
+
+    n_dev = gpu.lib.NcrDeviceCount()
+    assert n_dev >= 1
+    devices = [0, 1 % n_dev]
+    tex = gpu.Texture.from_numpy(image_rgba)           # lives on the default device
+    want = None
+    for d in sorted(set(devices)):
+        p = gpu.lib.NcrCreateRenderContextOnDevice(96, 64, True, d)
+        assert p and gpu.lib.NcrContextDevice(p) == d
+        ctx = gpu.context_from_ptr(p, 96, 64, True)
+        streams.stream_k1(ctx, tex, n=40)
+        got = cases.digest(ctx)
+        want = want or got
+        assert got == want
+    assert not gpu.lib.NcrCreateRenderContextOnDevice(8, 8, True, n_dev)   # out of range: NULL + error text
+    assert "device" in gpu.last_error()
+
+    w, h = 320, 180
+    chart = streams.make_chart_textures()
+    bg = np.ascontiguousarray(np.resize(streams.make_noise_texture(64, 7), (h, w, 4)))
+    tex_np = [bg] + chart
+    slots = [trace.TexSlot(k, t.shape[1], t.shape[0]) for k, t in enumerate(tex_np)]
+    traces = []
+    for f in range(11):
+        rec = trace.TraceRecorder(w, h, False)
+        streams.stream_c4_frame(rec, slots[0], slots[1:], frame=13 * f, n_notes=40, n_fx=6)
+        rec.present()
+        traces.append(rec.as_array())
+    texs = [gpu.Texture.from_numpy(t) for t in tex_np]
+    one, many = [], []
+    with batch.FramePool(gpu, w, h, False, workers=2) as pool:
+        assert pool.render(traces, texs, on_frame=lambda i, px: one.append((i, px.tobytes()))) == 11
+    with batch.FramePool(gpu, w, h, False, workers=4, devices=devices) as pool:
+        for present in ("u8", "yuv420p"):
+            many.clear()
+            assert pool.render(traces, texs, on_frame=lambda i, px: many.append((i, px.tobytes())), present=present) == 11
+            assert [i for i, _ in many] == list(range(11))
+            if present == "u8":
+                assert many == one
+
+
+# ---- every BASELINE configuration at its full size against digests of the UNMODIFIED reference build -----------------------
+def _bench_module():
+    import sys
+
+    from conftest import ROOT
+
+    sys.path.insert(0, ROOT)
+    import bench
+
+    return bench
+
+
+@pytest.mark.parametrize("workload", ["c1", "c2", "c3", "c4", "c5", "bg"])
+def test_full_size_workload_matches_the_reference_digest(workload, gpu):
+    """bench.py's workloads (BASELINE configs 1-5 + the low-overdraw frame) at their full sizes — incl. C2's 20,000 draws and
+    the 4K RGB chart frame of config 5 — rendered through the C ABI; the RGB(A)8 frame must hash to the digest of the
+    unmodified reference build (tests/golden/bench_golden.json, generated by tests/golden/make_bench_golden.py)."""
+    from conftest import REPLAY_LIB
+
+    bench = _bench_module()
+    want = bench.load_golden()["workloads"][workload]["u8"]
+    w, h, alpha, tex_np, arr, draws, full = bench.build_workload(workload)
+    ctx = gpu.RenderContext(w, h, alpha)
+    tex = [gpu.Texture.from_numpy(t) for t in tex_np]
+    trace.Replayer(REPLAY_LIB, gpu.path).run(ctx, arr, tex)
+    assert cases.sha(ctx.get_buffer_as_uint8()) == want
+    f64 = ctx.get_buffer_np()                                   # the stale canvas, brought up to date on demand
+    scaled = f64 * 255
+    safe = np.where(np.abs(scaled) < 2 ** 31, scaled, 0)
+    assert cases.sha((np.trunc(safe).astype(np.int64) & 0xFF).astype(np.uint8).tobytes()) == want
+
+
+@pytest.mark.parametrize("name,frames", [("c4", [0, 123, 359, 719, 3600, 7199]), ("c5", [0, 123, 239, 479, 959, 1919])])
+def test_chart_video_frames_match_the_reference_digests(name, frames, gpu):
+    """Six frame indices of the 7,200-frame 1080p chart (config 4) and of the 4K chart (config 5), each rendered through the
+    frame pool exactly as the video legs of bench.py render them (u8 and YUV present), against the reference's digests."""
+    from libnativecpurenderer_b200 import batch
+
+    bench = _bench_module()
+    want = bench.load_golden()["video"][name]
+    w, h, alpha, _ = bench.WORKLOADS[name]
+    tex = [gpu.Texture.from_numpy(t) for t in bench.chart_textures(w, h)]
+    traces = [bench.build_video_frame(name, f)[4] for f in frames]
+    with batch.FramePool(gpu, w, h, alpha, workers=3) as pool:
+        for present, key in (("u8", "u8"), ("yuv420p", "yuv420p")):
+            got = {}
+            assert pool.render(traces, tex, on_frame=lambda i, px: got.__setitem__(i, cases.sha(px.tobytes())), present=present) == len(frames)
+            assert [got[i] for i in range(len(frames))] == [want[str(f)][key] for f in frames]
+
+
+def test_present_path_reproduces_libswscale(gpu):
+    """SURVEY 8-f1, pinned: the YUV 4:2:0 planes the product hands to the encoder are byte-identical to what a real libswscale
+    (9.1.100; committed fixtures, tests/golden/make_swscale_fixtures.py) produces for PutRendererContextFrame's call — through
+    the flush that has draws pending (composite + ncr_yuv420p) and through the one that has none (standalone conversion)."""
+    fx = cases.swscale_fixtures()
+    k = 0
+    while f"img_{k}" in fx:
+        img = fx[f"img_{k}"]
+        ctx = cases.canvas_holding_u8_image(gpu, img)
+        pending = ctx.get_buffer_as_yuv420p().tobytes()            # draws pending: present-only flush
+        assert pending == fx[f"yuv_{k}"].tobytes(), f"fixture {k} {img.shape}"
+        assert bytes(ctx.get_buffer_as_uint8()) == img.tobytes()
+        ctx.flush()
+        ctx.draw_rect(0, 0, 1, 1, 0, 0, 0, 0)                       # invalidates the cached planes without changing a pixel
+        ctx.flush()
+        assert ctx.get_buffer_as_yuv420p().tobytes() == pending    # nothing pending: converted from the canvas
+        k += 1
+    assert k >= 5
