@@ -1096,6 +1096,7 @@ static void fill_texture_fields(NcrContext* c, NcrCmd* cmd, const void* ptr, uin
     if (c->sampling == 1) cmd->flags |= NCR_F_BILINEAR;
     else if ((tflags & NCR_F_TEX_ALPHA) && !(tflags & NCR_F_TEX_F64) && tw * th < 0x7fffffffL) {
         cmd->flags |= NCR_F_TEX_FAST;
+        if (c->st.ct[3] >= 0.0 && c->st.ct[3] < 1.0) cmd->flags |= NCR_F_ALPHA_LT1;
         // the composite's hot path: DrawTexture, and DrawSplittedTexture on power-of-two textures (no division)
         if (cmd->op == NCR_OP_TEX || (cmd->op == NCR_OP_TEX_SPLIT && is_pow2(tw) && is_pow2(th))) cmd->flags |= NCR_F_FAST_AFFINE;
     }

@@ -227,7 +227,9 @@ struct Slots {
 
 // Shared tail of the textured ops: decode four RGBA8 texels and blend (straight-line, predicated).  RGB_ONE: the colour
 // transform's rgb are exactly 1.0, so r * 1.0 (cpp:525-527) is the identity and is not issued.
-template <bool ALPHA, bool COUNT, bool RGB_ONE>
+// NE_TRUE: the recorder proved a != 1 on every pixel (NCR_F_ALPHA_LT1): the blend is unconditional under `in`, and the plain-store
+// pass does not exist.
+template <bool ALPHA, bool COUNT, bool RGB_ONE, bool NE_TRUE = false>
 __device__ __forceinline__ void shade_rgba8(const NcrCmd& c, uint32_t lut_base, const uint32_t (&tx)[NCR_P], const bool (&in)[NCR_P],
                                             double (&dr)[NCR_P], double (&dg)[NCR_P], double (&db)[NCR_P], double (&da)[NCR_P],
                                             unsigned long long& n_applied) {
@@ -242,10 +244,18 @@ __device__ __forceinline__ void shade_rgba8(const NcrCmd& c, uint32_t lut_base, 
         double a = lut_byte<3>(lut_base, t);
         if (!RGB_ONE) { r = MUL(r, ct0); g = MUL(g, ct1); b = MUL(b, ct2); }   // cpp:525-527
         a = MUL(a, ct3);                                                       // cpp:528
-        opaque[p] = blend<ALPHA>(dr[p], dg[p], db[p], da[p], r, g, b, a, in[p]);
+        if (NE_TRUE) {
+            const double om = SUB(1.0, a);
+            padd(dr[p], MUL(dr[p], om), MUL(r, a), in[p]);
+            padd(dg[p], MUL(dg[p], om), MUL(g, a), in[p]);
+            padd(db[p], MUL(db[p], om), MUL(b, a), in[p]);
+            if (ALPHA) da[p] = in[p] ? a : da[p];
+        } else {
+            opaque[p] = blend<ALPHA>(dr[p], dg[p], db[p], da[p], r, g, b, a, in[p]);
+        }
         if (COUNT) n_applied += in[p] ? 1 : 0;
     }
-    if (__any_sync(FULL, any_slot(opaque))) {   // a == 1: the source is stored as is
+    if (!NE_TRUE && __any_sync(FULL, any_slot(opaque))) {   // a == 1: the source is stored as is
         FOR4 {
             const uint32_t t = tx[p];
             double r = lut_byte<0>(lut_base, t), g = lut_byte<1>(lut_base, t), b = lut_byte<2>(lut_base, t);
@@ -346,7 +356,9 @@ __device__ __forceinline__ void tex_fast(const NcrCmd& c, const uint32_t op, con
         const int yi = __vimin_s32_relu(__double2int_rz(v[p]), th2);
         tx[p] = (INTERIOR || in[p]) ? __ldg(t32 + (yi * tw + xi)) : 0u;
     }
-    if (flags & NCR_F_CT_RGB_ONE) shade_rgba8<ALPHA, COUNT, true>(c, lut_base, tx, in, dr, dg, db, da, n_applied);
+    if ((flags & (NCR_F_CT_RGB_ONE | NCR_F_ALPHA_LT1)) == (NCR_F_CT_RGB_ONE | NCR_F_ALPHA_LT1))
+        shade_rgba8<ALPHA, COUNT, true, true>(c, lut_base, tx, in, dr, dg, db, da, n_applied);
+    else if (flags & NCR_F_CT_RGB_ONE) shade_rgba8<ALPHA, COUNT, true>(c, lut_base, tx, in, dr, dg, db, da, n_applied);
     else shade_rgba8<ALPHA, COUNT, false>(c, lut_base, tx, in, dr, dg, db, da, n_applied);
 }
 

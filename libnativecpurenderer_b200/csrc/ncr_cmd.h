@@ -38,6 +38,8 @@ enum : uint32_t {
     NCR_F_SPLIT_POW2 = 1u << 7,   // TEX_SPLIT: texture width and height are powers of two; p[6], p[7] = 1/w, 1/h (exact)
     NCR_F_TEX_FAST = 1u << 8,     // RGBA8 texels, nearest sampling, fewer than 2^31 texels: inlined sampler
     NCR_F_FAST_AFFINE = 1u << 9,  // NCR_OP_TEX / NCR_OP_TEX_SPLIT with NCR_F_TEX_FAST: the composite's first-tested path
+    NCR_F_ALPHA_LT1 = 1u << 10,   // RGBA8 texture and 0 <= ct[3] < 1: a = fl(texel_a * ct3) <= ct3 < 1 for every texel (texel_a = k/255 <= 1,
+                                  // rounding is monotone), so `a != 1` (cpp:533) is true on every pixel: no test, no plain-store case
 };
 
 struct alignas(16) NcrCmd {

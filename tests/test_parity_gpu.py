@@ -853,3 +853,51 @@ def test_present_path_reproduces_libswscale(gpu):
         assert ctx.get_buffer_as_yuv420p().tobytes() == pending    # nothing pending: converted from the canvas
         k += 1
     assert k >= 5
+
+
+def test_non_default_device_leaves_device_0_untouched(gpu):
+    """with NCR_DEVICE=1 the recording path of a fresh worker thread (frame pool, replayer threads) used to allocate
+    pinned staging with device 0 current, creating a primary context on GPU 0 for every rank.  A process that renders on device 1
+    — pool workers, replayer threads and a per-call context — must not appear among GPU 0's compute processes (NVML).
+    Needs two visible devices (gpurun --gpus 2)."""
+    import subprocess
+    import sys
+
+    from conftest import REPLAY_LIB, ROOT
+
+    if gpu.lib.NcrDeviceCount() < 2:
+        pytest.skip("one visible device")
+    code = f"""
+import os, sys
+os.environ["NCR_DEVICE"] = "1"
+sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {ROOT + '/tests'!r})
+import numpy as np, pynvml
+from libnativecpurenderer_b200 import batch, streams, trace
+from libnativecpurenderer_b200.binding import Renderer
+pynvml.nvmlInit()
+used0_before = pynvml.nvmlDeviceGetMemoryInfo(pynvml.nvmlDeviceGetHandleByIndex(0)).used
+R = Renderer()
+w, h = 320, 180
+chart = streams.make_chart_textures()
+bg = np.ascontiguousarray(np.resize(streams.make_noise_texture(64, 7), (h, w, 4)))
+tex_np = [bg] + chart
+slots = [trace.TexSlot(k, t.shape[1], t.shape[0]) for k, t in enumerate(tex_np)]
+traces = []
+for f in range(9):
+    rec = trace.TraceRecorder(w, h, False); streams.stream_c4_frame(rec, slots[0], slots[1:], frame=f, n_notes=60, n_fx=6); rec.present(); traces.append(rec.as_array())
+tex = [R.Texture.from_numpy(t) for t in tex_np]
+assert batch.render_frames(R, w, h, False, traces, tex, workers=4) == 9
+trace.Replayer({REPLAY_LIB!r}, R.path).run_threads(4, w, h, False, traces[0], tex, repeats=2)
+ctx = R.RenderContext(64, 64, True); assert R.lib.NcrContextDevice(ctx._ptr) == 1
+streams.stream_k1(ctx, R.Texture.from_numpy(np.zeros((8, 8, 4), np.uint8)), n=20); ctx.get_buffer_as_uint8()
+pids0 = [p.pid for p in pynvml.nvmlDeviceGetComputeRunningProcesses(pynvml.nvmlDeviceGetHandleByIndex(0))]
+pids1 = [p.pid for p in pynvml.nvmlDeviceGetComputeRunningProcesses(pynvml.nvmlDeviceGetHandleByIndex(1))]
+grown0 = pynvml.nvmlDeviceGetMemoryInfo(pynvml.nvmlDeviceGetHandleByIndex(0)).used - used0_before
+print("ON0", os.getpid() in pids0, "ON1", os.getpid() in pids1, "GROWN0_MB", grown0 >> 20)
+"""
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = [l for l in res.stdout.splitlines() if l.startswith("ON0")][-1].split()
+    assert line[1] == "False", res.stdout                 # this process is not a compute process of GPU 0 ...
+    assert int(line[5]) < 64, res.stdout                  # ... and GPU 0's memory did not grow by a CUDA context (hundreds of MB)
+    # (line[3] is True where NVML reports container-local pids; in a pid namespace the memory check alone carries the test)
