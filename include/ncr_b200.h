@@ -193,6 +193,10 @@ long NcrFramePoolRender(NcrFramePool* pool, const void* const* traces, const lon
                         Texture* const* textures, long n_textures, int present, NcrFrameSink sink, void* user);
 long NcrYUV420PSize(RenderContext* ctx);
 long NcrGetBufferAsYUV420P(RenderContext* ctx, unsigned char* out);
+/* The scaling branch of PutRendererContextFrame (h:91 cpp:241-256: cap size != canvas size, sws_scale resizes with SWS_BILINEAR):
+ * the planes at dst_w x dst_h, Y[dst_h][dst_w], U, V[(dst_h+1)/2][(dst_w+1)/2]; returns the bytes written or -1.  Bit-identical to
+ * libswscale (pinned against 9.1.100) for source and destination sizes >= 16 with an even source width. */
+long NcrGetBufferAsYUV420PScaled(RenderContext* ctx, long dst_w, long dst_h, unsigned char* out);
 
 #ifdef __cplusplus
 }

@@ -90,6 +90,7 @@ _EXT_ABI = {
     "NcrCreateRenderContextOnDevice": (_P, (c_long, c_long, c_bool, c_int)),
     "NcrContextDevice": (c_int, (_P,)),
     "NcrCreateFramePoolOnDevices": (_P, (c_long, c_long, c_int, c_int, _P, c_int)),
+    "NcrGetBufferAsYUV420PScaled": (c_long, (_P, c_long, c_long, _P)),
     "NcrRerunLastFlush": (c_int, (_P, c_int, c_int, _P)),
     "NcrRerunLastFlushEx": (c_int, (_P, c_int, c_int, _P, c_int, c_int)),
     "NcrGetStats": (None, (_P, _P)),
@@ -399,6 +400,17 @@ class RenderContext:
         got = self._lib.NcrGetBufferAsYUV420P(self._ptr, _as_void_p(out))
         if got != n:
             raise RuntimeError("NcrGetBufferAsYUV420P failed")
+        return out
+
+    def get_buffer_as_yuv420p_scaled(self, dst_w: int, dst_h: int):
+        """The planes at another size: what PutRendererContextFrame hands the encoder when the VideoCap's size differs from the canvas's."""
+        import numpy as np
+
+        n = dst_w * dst_h + 2 * ((dst_w + 1) // 2) * ((dst_h + 1) // 2)
+        out = np.empty(n, dtype=np.uint8)
+        got = self._lib.NcrGetBufferAsYUV420PScaled(self._ptr, dst_w, dst_h, _as_void_p(out))
+        if got != n:
+            raise RuntimeError(f"NcrGetBufferAsYUV420PScaled returned {got}, expected {n}: {self._r.last_error()}")
         return out
 
     def get_buffer_as_yuv420p_into(self, address: int) -> int:

@@ -30,6 +30,7 @@
 #include "ncr_cmd.h"
 #include "ncr_trace.h"
 #include "state.h"
+#include "swscale_filter.h"
 
 // ------------------------------------------------------------------------------------------------
 // device bookkeeping
@@ -274,6 +275,13 @@ struct NcrContext {
     int stats_mode = 0;
     NcrStats stats;
     bool failed = false;   // sticky device error
+
+    // present path, scaling branch: filter tables of the last (canvas size -> dw x dh) conversion, kept on the device
+    NcrSwsPlan sws;
+    bool sws_valid = false;
+    DevVec<int32_t> d_sws_tables;
+    DevVec<short> d_sws_mid;
+    DevVec<unsigned char> d_sws_out;
 
     // experiment X5: the pending batch's TMA-stageable background draw (see NcrFlushArgs::tma_map)
     const void* tma_map = nullptr;
@@ -871,6 +879,7 @@ void DestroyRenderContext(RenderContext* ctx) {
     c->d_cmds.release(); c->d_boxes.release(); c->d_binbox.release(); c->d_aux.release();
     c->d_coarse.release(); c->d_coarse_off.release(); c->d_fine.release(); c->d_fine_off.release();
     c->d_cursors.release(); c->d_u8.release(); c->d_yuv.release();
+    c->d_sws_tables.release(); c->d_sws_mid.release(); c->d_sws_out.release();
     for (int k = 0; k < 2; ++k) {
         c->stg[k].cmds.release(); c->stg[k].boxes.release(); c->stg[k].binbox.release(); c->stg[k].aux.release();
         if (c->stg[k].done) cudaEventDestroy(c->stg[k].done);
@@ -925,11 +934,71 @@ long NcrYUV420PSize(RenderContext* ctx) {
 
 // Present path: the composite writes the YUV 4:2:0 planes of the (iu8)(v*255) image with its tiles (a standalone kernel does
 // it when nothing is pending); only the planes, 1.5 B/px, are read back.
+// libswscale-exact conversion of the current u8 image to dw x dh planes through the general (filter-table) path: the scaling
+// branch of PutRendererContextFrame (cap size != canvas size, cpp:241-256), and same-size conversions of odd / tiny canvases,
+// which the fused same-size kernel does not cover.  Leaves the planes in c->d_sws_out.
+static bool sws_general(NcrContext* c, long dw, long dh) {
+    if (!flush(c, true)) return false;   // composite (+ fused u8 image); the canvas write-back is skipped as for any present
+    const int w = (int)c->w, h = (int)c->h;
+    if (!c->sws_valid || c->sws.w != w || c->sws.h != h || c->sws.dw != dw || c->sws.dh != dh) {
+        NcrSwsPlan P;
+        memset(&P, 0, sizeof(P));
+        P.w = w; P.h = h; P.dw = (int)dw; P.dh = (int)dh;
+        P.cdw = (int)((dw + 1) / 2); P.cdh = (int)((dh + 1) / 2);
+        P.half = ((dw >> 1) <= (w >> 1)) ? 1 : 0;              // libswscale: chroma input at half width unless the output needs more
+        P.cw = P.half ? (w + 1) / 2 : w;
+        const NcrSwsFilter hl = ncr_sws_make_filter(w, P.dw, 4, 1 << 14), vl = ncr_sws_make_filter(h, P.dh, 2, 1 << 12);
+        const NcrSwsFilter hc = ncr_sws_make_filter(P.cw, P.cdw, 4, 1 << 14), vc = ncr_sws_make_filter(h, P.cdh, 2, 1 << 12);
+        std::vector<int32_t> all;
+        size_t off[8];
+        const std::vector<int32_t>* parts[8] = {&hl.pos, &hl.coef, &vl.pos, &vl.coef, &hc.pos, &hc.coef, &vc.pos, &vc.coef};
+        for (int k = 0; k < 8; ++k) { off[k] = all.size(); all.insert(all.end(), parts[k]->begin(), parts[k]->end()); }
+        if (!sync_ctx(c) || !c->d_sws_tables.reserve(all.size())) return false;   // the previous tables may still be in use
+        if (!CK(cudaMemcpyAsync(c->d_sws_tables.p, all.data(), all.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream)) ||
+            !CK(cudaStreamSynchronize(c->stream)))
+            return false;
+        const int32_t* base = c->d_sws_tables.p;
+        P.hl_pos = base + off[0]; P.hl_coef = base + off[1]; P.vl_pos = base + off[2]; P.vl_coef = base + off[3];
+        P.hc_pos = base + off[4]; P.hc_coef = base + off[5]; P.vc_pos = base + off[6]; P.vc_coef = base + off[7];
+        P.hl_size = hl.size; P.vl_size = vl.size; P.hc_size = hc.size; P.vc_size = vc.size;
+        c->sws = P;
+        c->sws_valid = true;
+    }
+    const NcrSwsPlan& P = c->sws;
+    const size_t mid_y = (size_t)P.h * P.dw, mid_c = (size_t)P.h * P.cdw;
+    if (!c->d_sws_mid.reserve(mid_y + 2 * mid_c) || !c->d_sws_out.reserve((size_t)P.dw * P.dh + 2 * (size_t)P.cdw * P.cdh)) return false;
+    ncr_launch_sws_scaled(c->d_u8.p, ipp_of(c), &P, c->d_sws_mid.p, c->d_sws_mid.p + mid_y, c->d_sws_mid.p + mid_y + mid_c,
+                          c->d_sws_out.p, c->stream);
+    g_launches += 2;
+    c->stats.kernel_launches += 2;
+    return CK(cudaGetLastError());
+}
+
+long NcrGetBufferAsYUV420PScaled(RenderContext* ctx, long dst_w, long dst_h, unsigned char* out) {
+    NcrContext* c = live(ctx);
+    if (!c || !out || dst_w <= 0 || dst_h <= 0 || dst_w > 0x3fffffff || dst_h > 0x3fffffff) return -1;
+    if (c->w <= 0 || c->h <= 0) return 0;
+    if (dst_w == c->w && dst_h == c->h && !(c->w & 1) && !(c->h & 1) && c->w >= 8 && c->h >= 8) return NcrGetBufferAsYUV420P(ctx, out);
+    if (!sws_general(c, dst_w, dst_h)) { c->failed = true; return -1; }
+    const long bytes = dst_w * dst_h + 2 * ((dst_w + 1) / 2) * ((dst_h + 1) / 2);
+    if (!CK(cudaMemcpyAsync(out, c->d_sws_out.p, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream))) { c->failed = true; return -1; }
+    c->stats.d2h_bytes += (size_t)bytes;
+    return sync_ctx(c) ? bytes : -1;
+}
+
+// Present path: the composite writes the (iu8)(v*255) image with its regions and ncr_yuv420p converts it (a standalone pass when
+// nothing is pending); only the planes, 1.5 B/px, are read back.
 long NcrGetBufferAsYUV420P(RenderContext* ctx, unsigned char* out) {
     NcrContext* c = live(ctx);
     if (!c || !out) return -1;
     const long bytes = NcrYUV420PSize(ctx);
     if (bytes <= 0) return 0;
+    if ((c->w & 1) || (c->h & 1) || c->w < 8 || c->h < 8) {   // odd / tiny canvases: the general path (same tables as libswscale builds)
+        if (!sws_general(c, c->w, c->h)) { c->failed = true; return -1; }
+        if (!CK(cudaMemcpyAsync(out, c->d_sws_out.p, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream))) { c->failed = true; return -1; }
+        c->stats.d2h_bytes += (size_t)bytes;
+        return sync_ctx(c) ? bytes : -1;
+    }
     if (!flush(c, false, true)) return -1;
     if (!CK(cudaGetLastError()) ||
         !CK(cudaMemcpyAsync(out, c->d_yuv.p, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream))) { c->failed = true; return -1; }

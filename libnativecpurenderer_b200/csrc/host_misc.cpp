@@ -227,10 +227,11 @@ void PutRendererContextFrame(VideoCap* cap, RenderContext* ctx) {
     if (!cap || !ctx) return;
     // cpp:232-256: f64 -> u8 truncation, then RGB(A) -> YUV420P for the encoder.  Both steps run on the device and only
     // the planes (1.5 B/px) come back; with no encoder linked (FFmpeg absent) the frame is kept as `last` and counted.
-    const long n = NcrYUV420PSize(ctx);
-    if (n <= 0) return;
+    // cap size != canvas size: libswscale resizes while converting (sws_getContext(ctx w, h -> cap w, h, SWS_BILINEAR), cpp:241-246)
+    if (cap->width <= 0 || cap->height <= 0) return;
+    const long n = cap->width * cap->height + 2 * ((cap->width + 1) / 2) * ((cap->height + 1) / 2);
     cap->last.resize((size_t)n);
-    if (NcrGetBufferAsYUV420P(ctx, cap->last.data()) != n) return;
+    if (NcrGetBufferAsYUV420PScaled(ctx, cap->width, cap->height, cap->last.data()) != n) return;
     cap->frames += 1;
 }
 

@@ -401,6 +401,91 @@ extern "C" void ncr_launch_yuv420p(const unsigned char* img, unsigned char* out,
     else ncr_yuv420p<3, 1><<<grid, 256, 0, s>>>(img, out, w, h);
 }
 
+// ---- present path, scaling branch: cap size != canvas size (reference cpp:241-256 lets sws_scale resize) --------------------------
+// Two passes with the filter tables the host builds (csrc/swscale_filter.h = libswscale's initFilter for SWS_BILINEAR):
+//   horizontal  (x86 hscale14to15) per source row: out15 = min((sum_j s14[pos + j] * f[j]) >> 13, 32767), with s14 the 14-bit luma
+//               / chroma of the u8 image (chroma from pixel-pair sums when `half`, else full width) evaluated on the fly;
+//   vertical    one tap: (v15 + 64) >> 7; else the 16-bit SIMD scaler acc = ((64 + 8 (n - 1)) >> 4) + sum_j ((v15 * f[j]) >> 16),
+//               out = acc >> 3 — except the last two luma rows / the last chroma row, which libswscale's C scaler produces:
+//               ((64 << 12) + sum_j v15 * f[j]) >> 19.
+// Bit-exact against libswscale 9.1.100 (tests: fixtures + live), see oracle/ncr_oracle.c for the restatement of the same algorithm.
+template <int IPP>
+__global__ void __launch_bounds__(256) ncr_sws_horizontal(const unsigned char* __restrict__ img, NcrSwsPlan P, short* __restrict__ mid_y,
+                                                          short* __restrict__ mid_u, short* __restrict__ mid_v) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (y >= P.h) return;
+    const unsigned char* row = img + (size_t)y * P.w * IPP;
+    if (x < P.dw) {
+        long long acc = 0;
+        const int p0 = P.hl_pos[x];
+        for (int j = 0; j < P.hl_size; ++j) {
+            const unsigned char* q = row + (size_t)min(p0 + j, P.w - 1) * IPP;   // a clamped index only ever meets a zero coefficient
+            const int y14 = (8414 * q[0] + 16519 * q[1] + 3208 * q[2] + (32 << 14) + (1 << 8)) >> 9;
+            acc += (long long)y14 * P.hl_coef[x * P.hl_size + j];
+        }
+        mid_y[(size_t)y * P.dw + x] = (short)min(acc >> 13, 32767ll);
+    }
+    if (x < P.cdw) {
+        long long au = 0, av = 0;
+        const int p0 = P.hc_pos[x];
+        for (int j = 0; j < P.hc_size; ++j) {
+            const int sx = min(p0 + j, P.cw - 1);
+            int u14, v14;
+            if (P.half) {
+                const unsigned char *a = row + (size_t)(2 * sx) * IPP, *b = row + (size_t)min(2 * sx + 1, P.w - 1) * IPP;
+                const int r2 = a[0] + b[0], g2 = a[1] + b[1], b2 = a[2] + b[2];
+                u14 = (-4865 * r2 - 9528 * g2 + 14392 * b2 + (0x4001 << 9)) >> 10;
+                v14 = (14392 * r2 - 12061 * g2 - 2332 * b2 + (0x4001 << 9)) >> 10;
+            } else {
+                const unsigned char* a = row + (size_t)sx * IPP;
+                u14 = (-4865 * a[0] - 9528 * a[1] + 14392 * a[2] + (256 << 14) + (1 << 8)) >> 9;
+                v14 = (14392 * a[0] - 12061 * a[1] - 2332 * a[2] + (256 << 14) + (1 << 8)) >> 9;
+            }
+            const int c = P.hc_coef[x * P.hc_size + j];
+            au += (long long)u14 * c;
+            av += (long long)v14 * c;
+        }
+        mid_u[(size_t)y * P.cdw + x] = (short)min(au >> 13, 32767ll);
+        mid_v[(size_t)y * P.cdw + x] = (short)min(av >> 13, 32767ll);
+    }
+}
+
+__device__ __forceinline__ unsigned char ncr_sws_vtap(const short* __restrict__ mid, int stride, int src_h, int x, int y, int dst_h,
+                                                      const int32_t* __restrict__ pos, const int32_t* __restrict__ coef, int size, int c_rows) {
+    const int p0 = pos[y];
+    if (size == 1) return ncr_clip8((mid[(size_t)p0 * stride + x] + 64) >> 7);
+    if (y >= dst_h - c_rows) {
+        long long acc = 64ll << 12;
+        for (int j = 0; j < size; ++j) acc += (long long)mid[(size_t)min(p0 + j, src_h - 1) * stride + x] * coef[y * size + j];
+        return ncr_clip8((int)(acc >> 19));
+    }
+    int acc = (64 + 8 * (size - 1)) >> 4;
+    for (int j = 0; j < size; ++j) acc += (mid[(size_t)min(p0 + j, src_h - 1) * stride + x] * coef[y * size + j]) >> 16;
+    return ncr_clip8(acc >> 3);
+}
+
+__global__ void __launch_bounds__(256) ncr_sws_vertical(NcrSwsPlan P, const short* __restrict__ mid_y, const short* __restrict__ mid_u,
+                                                        const short* __restrict__ mid_v, unsigned char* __restrict__ out) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    unsigned char* Y = out;
+    unsigned char* U = out + (size_t)P.dw * P.dh;
+    unsigned char* V = U + (size_t)P.cdw * P.cdh;
+    if (x < P.dw && y < P.dh) Y[(size_t)y * P.dw + x] = ncr_sws_vtap(mid_y, P.dw, P.h, x, y, P.dh, P.vl_pos, P.vl_coef, P.vl_size, 2);
+    if (x < P.cdw && y < P.cdh) {
+        U[(size_t)y * P.cdw + x] = ncr_sws_vtap(mid_u, P.cdw, P.h, x, y, P.cdh, P.vc_pos, P.vc_coef, P.vc_size, 1);
+        V[(size_t)y * P.cdw + x] = ncr_sws_vtap(mid_v, P.cdw, P.h, x, y, P.cdh, P.vc_pos, P.vc_coef, P.vc_size, 1);
+    }
+}
+
+extern "C" void ncr_launch_sws_scaled(const unsigned char* img, int ipp, const void* plan_, short* mid_y, short* mid_u, short* mid_v,
+                                      unsigned char* out, cudaStream_t s) {
+    const NcrSwsPlan& P = *(const NcrSwsPlan*)plan_;
+    dim3 gh((max(P.dw, P.cdw) + 31) / 32, (P.h + 7) / 8), gv((P.dw + 31) / 32, (P.dh + 7) / 8);
+    if (ipp == 4) ncr_sws_horizontal<4><<<gh, 256, 0, s>>>(img, P, mid_y, mid_u, mid_v);
+    else ncr_sws_horizontal<3><<<gh, 256, 0, s>>>(img, P, mid_y, mid_u, mid_v);
+    ncr_sws_vertical<<<gv, 256, 0, s>>>(P, mid_y, mid_u, mid_v, out);
+}
+
 extern "C" void ncr_launch_resample(const NcrCmd* src, void* out, int ow, int oh, cudaStream_t s) {
     dim3 grid((ow + 15) / 16, (oh + 15) / 16);
     ncr_resample<<<grid, 256, 0, s>>>(*src, out, ow, oh);

@@ -596,63 +596,225 @@ void NcrDrawTexturePerspective(Canvas* c, Image* tex, const f64* hinv, f64 x, f6
  *               (pmulhw per tap; the bias term compensates its truncation); the LAST chroma row is produced by the C
  *               scaler (swscale.c switches for dstY >= dstH - 2): U = clip8(((64 << 12) + sum_k U15[k] * coeff[k]) >> 19). */
 static u8 clip8(i64 v) { return (u8)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+
+/* The scaling branch (cap size != canvas size) goes through the same machinery with non-trivial filters, so the conversion is
+ * written once, for w x h -> dw x dh:
+ *   filters    libswscale/utils.c initFilter for SWS_BILINEAR: xInc = ((src << 16) + (dst >> 1)) / dst; |xInc - 65536| < 10 -> one unit
+ *              tap per output; else filterSize = 1 + 2 (upscale) or 1 + (2 src + dst - 1) / dst, taps = max(0, 2^30 - |distance|)
+ *              scaled by dst/src when shrinking, near-zero ends trimmed (cutoff 0.002), size rounded up to the SIMD alignment
+ *              (4 horizontal, 2 vertical on x86), out-of-image taps folded onto the edge, normalised to 2^14 (horizontal) or 2^12
+ *              (vertical) with error diffusion.  Chroma source is the pixel-PAIR sum when (dw >> 1) <= (w >> 1), else full width.
+ *   horizontal out15 = min((sum_j src14[pos + j] * f[j]) >> 13, 32767)                                     (x86 hscale14to15)
+ *   vertical   one tap: (v15 + 64) >> 7; else the 16-bit SIMD scaler acc = ((64 + 8 (n - 1)) >> 4) + sum_j ((v15[j] * f[j]) >> 16),
+ *              out = acc >> 3 — except the last two luma rows and the last chroma row, which the C scaler produces:
+ *              ((64 << 12) + sum_j v15[j] * f[j]) >> 19.
+ * Pinned against libswscale 9.1.100 for shrinking and enlarging, odd and even sizes (tests/test_oracle.py); with an odd SOURCE width
+ * on the pair-sum path libswscale reads one pixel past the row end — here the edge pixel is repeated (not pinned). */
+typedef struct { int size; int n; int* pos; int* coef; } SwsFilter;   /* coef[i * size + j] */
+
+static i64 sws_cdiv(i64 a, i64 b) { return a / b; }   /* C division truncates toward zero, as in libswscale */
+static i64 sws_rounded_div(i64 a, i64 b) { return (a >= 0 ? a + (b >> 1) : a - (b >> 1)) / b; }
+static int sws_log2(i64 v) { int n = 0; while (v > 1) { v >>= 1; ++n; } return n; }
+
+static int sws_init_filter(SwsFilter* F, i64 xInc, int srcW, int dstW, int align, i64 one) {
+    const i64 fone = (i64)1 << (54 - (sws_log2(srcW / dstW) < 8 ? sws_log2(srcW / dstW) : 8));
+    int fs, i, j;
+    i64* f;
+    int* pos = (int*)malloc((size_t)dstW * sizeof(int));
+    if (!pos) return -1;
+    if (llabs(xInc - 0x10000) < 10) {   /* unscaled (source and destination sample positions coincide for every plane here) */
+        fs = 1;
+        f = (i64*)malloc((size_t)dstW * sizeof(i64));
+        if (!f) { free(pos); return -1; }
+        for (i = 0; i < dstW; ++i) { f[i] = fone; pos[i] = i; }
+    } else {
+        i64 xDstInSrc = ((128 * xInc) >> 7) - ((128 * (i64)0x10000) >> 7);   /* srcPos = dstPos = 128 */
+        fs = (xInc <= (1 << 16)) ? 3 : (int)(1 + (2 * (i64)srcW + dstW - 1) / dstW);
+        if (fs > srcW - 2) fs = srcW - 2;
+        if (fs < 1) fs = 1;
+        f = (i64*)malloc((size_t)dstW * fs * sizeof(i64));
+        if (!f) { free(pos); return -1; }
+        for (i = 0; i < dstW; ++i) {
+            i64 xx = sws_cdiv(xDstInSrc - (fs - 2) * ((i64)1 << 16), (i64)1 << 17);
+            pos[i] = (int)xx;
+            for (j = 0; j < fs; ++j) {
+                i64 d = llabs(xx * ((i64)1 << 17) - xDstInSrc) << 13, coeff;
+                if (xInc > (1 << 16)) d = sws_cdiv(d * dstW, srcW);
+                coeff = ((i64)1 << 30) - d;
+                if (coeff < 0) coeff = 0;
+                coeff *= fone >> 30;
+                f[i * fs + j] = coeff;
+                ++xx;
+            }
+            xDstInSrc += 2 * xInc;
+        }
+    }
+    /* trim near-zero ends (SWS_MAX_REDUCE_CUTOFF = 0.002) and find the common size */
+    int minSize = 0;
+    for (i = dstW - 1; i >= 0; --i) {
+        int mn = fs;
+        double cut = 0;
+        for (j = 0; j < fs; ++j) {
+            cut += (double)llabs(f[i * fs]);
+            if (cut > 0.002 * (double)fone) break;
+            if (i < dstW - 1 && pos[i] >= pos[i + 1]) break;
+            memmove(&f[i * fs], &f[i * fs + 1], (size_t)(fs - 1) * sizeof(i64));
+            f[i * fs + fs - 1] = 0;
+            pos[i]++;
+        }
+        cut = 0;
+        for (j = fs - 1; j > 0; --j) {
+            cut += (double)llabs(f[i * fs + j]);
+            if (cut > 0.002 * (double)fone) break;
+            --mn;
+        }
+        if (mn > minSize) minSize = mn;
+    }
+    if (minSize == 1 && align == 2) align = 1;
+    const int size = (minSize + (align - 1)) & ~(align - 1);
+    i64* g = (i64*)calloc((size_t)dstW * size, sizeof(i64));
+    int* coef = (int*)malloc((size_t)dstW * size * sizeof(int));
+    if (!g || !coef) { free(f); free(pos); free(g); free(coef); return -1; }
+    for (i = 0; i < dstW; ++i)
+        for (j = 0; j < size; ++j) g[i * size + j] = j < fs ? f[i * fs + j] : 0;
+    free(f);
+    for (i = 0; i < dstW; ++i) {   /* fold taps that fall outside the image onto the edge */
+        i64* r = &g[i * size];
+        if (pos[i] < 0) {
+            for (j = 1; j < size; ++j) {
+                int left = j + pos[i] > 0 ? j + pos[i] : 0;
+                r[left] += r[j];
+                r[j] = 0;
+            }
+            pos[i] = 0;
+        }
+        if (pos[i] + size > srcW) {
+            int shift = pos[i] + (size - srcW < 0 ? size - srcW : 0);
+            i64 acc = 0;
+            for (j = size - 1; j >= 0; --j)
+                if (pos[i] + j >= srcW) { acc += r[j]; r[j] = 0; }
+            for (j = size - 1; j >= 0; --j) r[j] = j < shift ? 0 : r[j - shift];
+            pos[i] -= shift;
+            r[srcW - 1 - pos[i]] += acc;
+        }
+    }
+    for (i = 0; i < dstW; ++i) {   /* normalise to `one` with error diffusion */
+        i64 err = 0, sum = 0;
+        for (j = 0; j < size; ++j) sum += g[i * size + j];
+        sum = (sum + one / 2) / one;
+        if (!sum) sum = 1;
+        for (j = 0; j < size; ++j) {
+            i64 v = g[i * size + j] + err;
+            i64 q = sws_rounded_div(v, sum);
+            coef[i * size + j] = (int)q;
+            err = v - q * sum;
+        }
+    }
+    free(g);
+    F->size = size; F->n = dstW; F->pos = pos; F->coef = coef;
+    return 0;
+}
+static void sws_free_filter(SwsFilter* F) { free(F->pos); free(F->coef); F->pos = F->coef = NULL; }
+
+/* one plane: src14 [srcH][srcW] -> horizontal (H) -> vertical (V) -> dst [dstH][dstW]; c_rows = rows at the bottom done by the C scaler */
+static int sws_plane(const int* src14, int srcW, int srcH, const SwsFilter* H, const SwsFilter* V, int c_rows, u8* dst) {
+    const int dstW = H->n, dstH = V->n;
+    int* mid = (int*)malloc((size_t)srcH * dstW * sizeof(int));
+    if (!mid) return -1;
+    for (int y = 0; y < srcH; ++y)
+        for (int x = 0; x < dstW; ++x) {
+            i64 acc = 0;
+            for (int j = 0; j < H->size; ++j) {
+                int sx = H->pos[x] + j;
+                if (sx > srcW - 1) sx = srcW - 1;   /* only ever multiplies a zero coefficient */
+                acc += (i64)src14[y * srcW + sx] * H->coef[x * H->size + j];
+            }
+            acc >>= 13;
+            mid[y * dstW + x] = (int)(acc > 32767 ? 32767 : acc);
+        }
+    for (int y = 0; y < dstH; ++y)
+        for (int x = 0; x < dstW; ++x) {
+            i64 acc;
+            if (V->size == 1) {
+                acc = ((i64)mid[V->pos[y] * dstW + x] + 64) >> 7;
+            } else if (y >= dstH - c_rows) {
+                acc = (i64)64 << 12;
+                for (int j = 0; j < V->size; ++j) {
+                    int sy = V->pos[y] + j;
+                    if (sy > srcH - 1) sy = srcH - 1;
+                    acc += (i64)mid[sy * dstW + x] * V->coef[y * V->size + j];
+                }
+                acc >>= 19;
+            } else {
+                acc = (64 + 8 * (V->size - 1)) >> 4;
+                for (int j = 0; j < V->size; ++j) {
+                    int sy = V->pos[y] + j;
+                    if (sy > srcH - 1) sy = srcH - 1;
+                    acc += ((i64)mid[sy * dstW + x] * V->coef[y * V->size + j]) >> 16;
+                }
+                acc >>= 3;
+            }
+            dst[y * dstW + x] = clip8(acc);
+        }
+    free(mid);
+    return 0;
+}
+
+static long yuv420p_of(Canvas* c, i64 dw, i64 dh, u8* out) {
+    const i64 w = c->w, h = c->h, cdw = (dw + 1) / 2, cdh = (dh + 1) / 2;
+    const int ipp = c->ipp;
+    if (w <= 0 || h <= 0 || dw <= 0 || dh <= 0) return 0;
+    const int half = (dw >> 1) <= (w >> 1);          /* chroma input: pixel-pair sums, else full width */
+    const i64 cw = half ? (w + 1) / 2 : w;
+    u8* img = (u8*)malloc((size_t)(w * h * ipp));
+    int* y14 = (int*)malloc((size_t)(w * h) * sizeof(int));
+    int* u14 = (int*)malloc((size_t)(cw * h) * sizeof(int));
+    int* v14 = (int*)malloc((size_t)(cw * h) * sizeof(int));
+    SwsFilter hl = {0}, vl = {0}, hc = {0}, vc = {0};
+    long rc = -1;
+    if (!img || !y14 || !u14 || !v14) goto done;
+    GetBufferAsUInt8(c, img);
+    for (i64 j = 0; j < h; ++j) {
+        for (i64 i = 0; i < w; ++i) {
+            const u8* q = img + (j * w + i) * ipp;
+            y14[j * w + i] = (int)((8414 * (i64)q[0] + 16519 * (i64)q[1] + 3208 * (i64)q[2] + (32 << 14) + (1 << 8)) >> 9);
+        }
+        for (i64 i = 0; i < cw; ++i) {
+            if (half) {
+                const i64 x0 = 2 * i, x1 = (2 * i + 1 < w) ? 2 * i + 1 : w - 1;
+                const u8 *p0 = img + (j * w + x0) * ipp, *p1 = img + (j * w + x1) * ipp;
+                const i64 r2 = p0[0] + p1[0], g2 = p0[1] + p1[1], b2 = p0[2] + p1[2];
+                u14[j * cw + i] = (int)((-4865 * r2 - 9528 * g2 + 14392 * b2 + ((i64)0x4001 << 9)) >> 10);
+                v14[j * cw + i] = (int)((14392 * r2 - 12061 * g2 - 2332 * b2 + ((i64)0x4001 << 9)) >> 10);
+            } else {
+                const u8* q = img + (j * w + i) * ipp;
+                u14[j * cw + i] = (int)((-4865 * (i64)q[0] - 9528 * (i64)q[1] + 14392 * (i64)q[2] + (256 << 14) + (1 << 8)) >> 9);
+                v14[j * cw + i] = (int)((14392 * (i64)q[0] - 12061 * (i64)q[1] - 2332 * (i64)q[2] + (256 << 14) + (1 << 8)) >> 9);
+            }
+        }
+    }
+    if (sws_init_filter(&hl, (((i64)w << 16) + (dw >> 1)) / dw, (int)w, (int)dw, 4, 1 << 14) ||
+        sws_init_filter(&vl, (((i64)h << 16) + (dh >> 1)) / dh, (int)h, (int)dh, 2, 1 << 12) ||
+        sws_init_filter(&hc, (((i64)cw << 16) + (cdw >> 1)) / cdw, (int)cw, (int)cdw, 4, 1 << 14) ||
+        sws_init_filter(&vc, (((i64)h << 16) + (cdh >> 1)) / cdh, (int)h, (int)cdh, 2, 1 << 12))
+        goto done;
+    {
+        u8 *Y = out, *U = out + dw * dh, *V = U + cdw * cdh;
+        if (sws_plane(y14, (int)w, (int)h, &hl, &vl, 2, Y) || sws_plane(u14, (int)cw, (int)h, &hc, &vc, 1, U) ||
+            sws_plane(v14, (int)cw, (int)h, &hc, &vc, 1, V))
+            goto done;
+    }
+    rc = (long)(dw * dh + 2 * cdw * cdh);
+done:
+    sws_free_filter(&hl); sws_free_filter(&vl); sws_free_filter(&hc); sws_free_filter(&vc);
+    free(img); free(y14); free(u14); free(v14);
+    return rc;
+}
+
 long NcrYUV420PSize(Canvas* c) {
     if (c->w <= 0 || c->h <= 0) return 0;
     return (long)(c->w * c->h + 2 * ((c->w + 1) / 2) * ((c->h + 1) / 2));
 }
-long NcrGetBufferAsYUV420P(Canvas* c, u8* out) {
-    const i64 w = c->w, h = c->h, cw = (w + 1) / 2, ch = (h + 1) / 2;
-    const int ipp = c->ipp;
-    if (w <= 0 || h <= 0) return 0;
-    u8* img = (u8*)malloc((size_t)(w * h * ipp));
-    int* u15 = (int*)malloc((size_t)(h * cw) * sizeof(int));
-    int* v15 = (int*)malloc((size_t)(h * cw) * sizeof(int));
-    if (!img || !u15 || !v15) { free(img); free(u15); free(v15); return -1; }
-    GetBufferAsUInt8(c, img);
-    u8 *Y = out, *U = out + w * h, *V = U + cw * ch;
-    for (i64 j = 0; j < h; ++j) {
-        for (i64 i = 0; i < w; ++i) {
-            const u8* q = img + (j * w + i) * ipp;
-            const i64 y14 = (8414 * (i64)q[0] + 16519 * (i64)q[1] + 3208 * (i64)q[2] + (32 << 14) + (1 << 8)) >> 9;
-            Y[j * w + i] = clip8(((y14 << 1) + 64) >> 7);
-        }
-        for (i64 i = 0; i < cw; ++i) {
-            const i64 x0 = 2 * i, x1 = (2 * i + 1 < w) ? 2 * i + 1 : w - 1;
-            const u8 *p0 = img + (j * w + x0) * ipp, *p1 = img + (j * w + x1) * ipp;
-            const i64 r2 = p0[0] + p1[0], g2 = p0[1] + p1[1], b2 = p0[2] + p1[2];
-            i64 u = ((-4865 * r2 - 9528 * g2 + 14392 * b2 + ((i64)0x4001 << 9)) >> 10) << 1;
-            i64 v = ((14392 * r2 - 12061 * g2 - 2332 * b2 + ((i64)0x4001 << 9)) >> 10) << 1;
-            u15[j * cw + i] = (int)(u > 32767 ? 32767 : u);
-            v15[j * cw + i] = (int)(v > 32767 ? 32767 : v);
-        }
-    }
-    static const int taps[4] = {512, 1536, 1536, 512};
-    for (i64 cj = 0; cj < ch; ++cj) {
-        /* rows 2cj-1 .. 2cj+2, out-of-image taps folded onto the edge row: at most 4 distinct rows */
-        i64 row[4]; int coef[4]; int n = 0;
-        for (int k = 0; k < 4; ++k) {
-            i64 y = 2 * cj - 1 + k;
-            if (y < 0) y = 0;
-            if (y > h - 1) y = h - 1;
-            if (n && row[n - 1] == y) coef[n - 1] += taps[k];
-            else { row[n] = y; coef[n] = taps[k]; ++n; }
-        }
-        const int last = (cj == ch - 1);
-        for (i64 i = 0; i < cw; ++i) {
-            i64 au, av;
-            if (last) {
-                au = av = (i64)64 << 12;
-                for (int k = 0; k < n; ++k) { au += (i64)u15[row[k] * cw + i] * coef[k]; av += (i64)v15[row[k] * cw + i] * coef[k]; }
-                au >>= 19; av >>= 19;
-            } else {
-                au = av = (64 + 8 * 3) >> 4;
-                for (int k = 0; k < n; ++k) { au += ((i64)u15[row[k] * cw + i] * coef[k]) >> 16; av += ((i64)v15[row[k] * cw + i] * coef[k]) >> 16; }
-                au >>= 3; av >>= 3;
-            }
-            U[cj * cw + i] = clip8(au);
-            V[cj * cw + i] = clip8(av);
-        }
-    }
-    free(img); free(u15); free(v15);
-    return NcrYUV420PSize(c);
-}
+long NcrGetBufferAsYUV420P(Canvas* c, u8* out) { return yuv420p_of(c, c->w, c->h, out); }
+/* cap size != canvas size: the sws_scale resize of cpp:241-256 */
+long NcrGetBufferAsYUV420PScaled(Canvas* c, long dst_w, long dst_h, u8* out) { return yuv420p_of(c, dst_w, dst_h, out); }

@@ -4,7 +4,8 @@ ctypes on a handful of images and stores inputs and outputs as fixtures.
 
     python tests/golden/make_swscale_fixtures.py        # needs a libswscale; uses the one bundled with opencv-python-headless
 
-Output (committed): swscale_fixtures.npz  (img_k, yuv_k arrays; `version` = libswscale version the fixtures came from).
+Output (committed): swscale_fixtures.npz  (img_k, yuv_k arrays; `scaled` = (image, dst_w, dst_h) rows with their syuv_n planes;
+`version` = libswscale version the fixtures came from).
 The reference pins no FFmpeg version; these fixtures are libswscale 9.1.100 (FFmpeg 8) on x86-64 (AVX2 host), no SWS flags
 beyond SWS_BILINEAR — i.e. the non-bitexact SIMD vertical scaler, which is what the reference runs."""
 import ctypes
@@ -50,23 +51,26 @@ def load_swscale():
     return sws, avutil
 
 
-def swscale_yuv420p(libs, img: np.ndarray) -> np.ndarray:
-    """img: (h, w, 3|4) uint8 -> planar Y, U, V concatenated, exactly as the reference's PutRendererContextFrame converts."""
+def swscale_yuv420p(libs, img: np.ndarray, dst_w: int | None = None, dst_h: int | None = None) -> np.ndarray:
+    """img: (h, w, 3|4) uint8 -> planar Y, U, V concatenated, exactly as the reference's PutRendererContextFrame converts
+    (dst_w x dst_h = the VideoCap's size; default: the canvas size)."""
     sws, avutil = libs
     h, w, c = img.shape
-    assert w % 2 == 0 and h % 2 == 0
+    dw, dh = dst_w or w, dst_h or h
     src_fmt = avutil.av_get_pix_fmt(b"rgba" if c == 4 else b"rgb24")
     dst_fmt = avutil.av_get_pix_fmt(b"yuv420p")
-    ctx = sws.sws_getContext(w, h, src_fmt, w, h, dst_fmt, SWS_BILINEAR, None, None, None)
+    ctx = sws.sws_getContext(w, h, src_fmt, dw, dh, dst_fmt, SWS_BILINEAR, None, None, None)
     assert ctx
-    src = np.ascontiguousarray(img)
-    out = np.zeros(w * h * 3 // 2, dtype=np.uint8)
-    y, u, v = out[: w * h], out[w * h: w * h * 5 // 4], out[w * h * 5 // 4:]
+    src = np.zeros(w * h * c + 64, dtype=np.uint8)     # libswscale reads a pixel past an odd-width row: keep that inside the buffer
+    src[: w * h * c] = np.ascontiguousarray(img).ravel()
+    cw, ch = (dw + 1) // 2, (dh + 1) // 2
+    out = np.zeros(dw * dh + 2 * cw * ch, dtype=np.uint8)
+    y, u, v = out[: dw * dh], out[dw * dh: dw * dh + cw * ch], out[dw * dh + cw * ch:]
     srcp = (ctypes.c_void_p * 4)(src.ctypes.data, None, None, None)
     srcs = (ctypes.c_int * 4)(w * c, 0, 0, 0)
     dstp = (ctypes.c_void_p * 4)(y.ctypes.data, u.ctypes.data, v.ctypes.data, None)
-    dsts = (ctypes.c_int * 4)(w, w // 2, w // 2, 0)
-    assert sws.sws_scale(ctx, srcp, srcs, 0, h, dstp, dsts) == h
+    dsts = (ctypes.c_int * 4)(dw, cw, cw, 0)
+    assert sws.sws_scale(ctx, srcp, srcs, 0, h, dstp, dsts) == dh
     sws.sws_freeContext(ctx)
     return out
 
@@ -92,6 +96,11 @@ def main():
     for k, img in enumerate(fixture_images()):
         out[f"img_{k}"] = img
         out[f"yuv_{k}"] = swscale_yuv420p(libs, img)
+    # the scaling branch (cap size != canvas size): shrink, enlarge, odd destination sizes, one axis only
+    scaled = [(0, 64, 48), (0, 48, 32), (1, 75, 51), (1, 26, 18), (4, 128, 96), (4, 64, 20), (2, 16, 8), (0, 96, 32), (0, 40, 64)]
+    out["scaled"] = np.array(scaled)
+    for n, (k, dw, dh) in enumerate(scaled):
+        out[f"syuv_{n}"] = swscale_yuv420p(libs, out[f"img_{k}"], dw, dh)
     np.savez_compressed(os.path.join(HERE, "swscale_fixtures.npz"), **out)
     print("libswscale", out["version"], "fixtures:", len(fixture_images()))
 

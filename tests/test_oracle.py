@@ -98,6 +98,20 @@ def test_yuv420p_restatement_reproduces_libswscale_fixtures(port):
     assert k >= 5
 
 
+def test_yuv420p_scaling_branch_reproduces_libswscale_fixtures(port):
+    """cap size != canvas size (cpp:241-256 lets sws_scale resize): shrinking, enlarging, odd destination sizes, one axis only —
+    the restatement's planes are byte-identical to the real library's (committed fixtures)."""
+    fx = cases.swscale_fixtures()
+    ctxs = {}
+    for n, (k, dw, dh) in enumerate(fx["scaled"]):
+        k, dw, dh = int(k), int(dw), int(dh)
+        if k not in ctxs:
+            ctxs[k] = cases.canvas_holding_u8_image(port, fx[f"img_{k}"])
+        got = ctxs[k].get_buffer_as_yuv420p_scaled(dw, dh)
+        assert got.tobytes() == fx[f"syuv_{n}"].tobytes(), f"fixture {n}: image {k} {fx[f'img_{k}'].shape} -> {dw}x{dh}"
+    assert len(fx["scaled"]) >= 8
+
+
 def test_yuv420p_restatement_matches_a_live_libswscale(port):
     """The same against whatever libswscale this machine has (the opencv wheel bundles one), on fresh random images at video
     sizes; skipped where none can be loaded."""
@@ -116,6 +130,10 @@ def test_yuv420p_restatement_matches_a_live_libswscale(port):
         img = rs.randint(0, 256, shape).astype(np.uint8)
         ctx = cases.canvas_holding_u8_image(port, img)
         assert ctx.get_buffer_as_yuv420p().tobytes() == mk.swscale_yuv420p(libs, img).tobytes(), shape
+        h, w, _ = shape
+        for dw, dh in ((w * 2 // 3, h * 2 // 3), (w * 3 // 2 + 1, h * 3 // 2 + 1), (w, max(2, h // 2)), (max(8, w // 3), h)):   # the scaling branch
+            if min(w, h, dw, dh) >= 16:   # pinned domain of the scaling branch (tiny planes take other SIMD tails in libswscale)
+                assert ctx.get_buffer_as_yuv420p_scaled(dw, dh).tobytes() == mk.swscale_yuv420p(libs, img, dw, dh).tobytes(), (shape, dw, dh)
 
 
 def test_yuv420p_known_answers_and_odd_sizes(port):

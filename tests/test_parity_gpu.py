@@ -901,3 +901,55 @@ print("ON0", os.getpid() in pids0, "ON1", os.getpid() in pids1, "GROWN0_MB", gro
     assert line[1] == "False", res.stdout                 # this process is not a compute process of GPU 0 ...
     assert int(line[5]) < 64, res.stdout                  # ... and GPU 0's memory did not grow by a CUDA context (hundreds of MB)
     # (line[3] is True where NVML reports container-local pids; in a pid namespace the memory check alone carries the test)
+
+
+def test_present_path_scaling_branch_reproduces_libswscale(gpu, port):
+    """cap size != canvas size (cpp:241-256: sws_scale resizes while converting): NcrGetBufferAsYUV420PScaled and
+    PutRendererContextFrame with a VideoCap of another size give the planes of the real libswscale — committed fixtures (shrink,
+    enlarge, odd destination sizes, one axis only), the live library at video sizes where it loads, and the C restatement on
+    odd / tiny shapes outside the pinned domain."""
+    import sys
+
+    from conftest import GOLDEN_DIR
+
+    fx = cases.swscale_fixtures()
+    ctxs = {}
+    for n, (k, dw, dh) in enumerate(fx["scaled"]):
+        k, dw, dh = int(k), int(dw), int(dh)
+        if k not in ctxs:
+            ctxs[k] = cases.canvas_holding_u8_image(gpu, fx[f"img_{k}"])
+        assert ctxs[k].get_buffer_as_yuv420p_scaled(dw, dh).tobytes() == fx[f"syuv_{n}"].tobytes(), (n, k, dw, dh)
+    # PutRendererContextFrame with a cap of another size drives the same path (h:91)
+    raw = ctypes.CDLL(gpu.path)
+    raw.CreateVideoCap.restype = ctypes.c_void_p
+    raw.CreateVideoCap.argtypes = (ctypes.c_long, ctypes.c_long, ctypes.c_double)
+    raw.PutRendererContextFrame.argtypes = (ctypes.c_void_p, ctypes.c_void_p)
+    cap = raw.CreateVideoCap(48, 32, 30.0)
+    d2h0 = ctxs[0].stats().d2h_bytes
+    raw.PutRendererContextFrame(cap, ctxs[0]._ptr)
+    assert ctxs[0].stats().d2h_bytes - d2h0 == 48 * 32 * 3 // 2
+    # live library, video sizes: 720p -> 1080p and 1080p -> 720p
+    sys.path.insert(0, GOLDEN_DIR)
+    import make_swscale_fixtures as mk
+
+    libs = mk.load_swscale()
+    rs = np.random.RandomState(5)
+    if libs is not None:
+        for (h, w, c), (dw, dh) in (((720, 1280, 3), (1920, 1080)), ((1080, 1920, 4), (1280, 720)), ((270, 480, 3), (854, 481))):
+            img = rs.randint(0, 256, (h, w, c)).astype(np.uint8)
+            ctx = gpu.RenderContext(w, h, c == 4)
+            ctx.set_color(0, 0, 0, 0)
+            tex = np.zeros((h + 1, w + 1, 4), dtype=np.uint8)
+            tex[:h, :w, :c] = img
+            tex[..., 3] = 255
+            ctx.draw_texture(gpu.Texture.from_numpy(tex), 0, 0, w + 1, h + 1)     # RGBA8 texels k/255 with a == 1: stored as they are
+            got_img = np.frombuffer(ctx.get_buffer_as_uint8(), dtype=np.uint8).reshape(h, w, c)
+            assert ctx.get_buffer_as_yuv420p_scaled(dw, dh).tobytes() == mk.swscale_yuv420p(libs, got_img, dw, dh).tobytes(), (w, h, dw, dh)
+    # odd / tiny shapes (this repo's definition outside the pinned domain): product == restatement
+    for (w, h, alpha), (dw, dh) in (((97, 61, False), (50, 33)), ((33, 20, True), (70, 41)), ((8, 3, True), (8, 3)), ((24, 5, False), (12, 9))):
+        outs = []
+        for R in (gpu, port):
+            ctx = R.RenderContext(w, h, alpha)
+            streams.stream_random(ctx, cases.tiny_textures(R, np.zeros((4, 4, 4), np.uint8)), 91, n=40)
+            outs.append(ctx.get_buffer_as_yuv420p_scaled(dw, dh).tobytes())
+        assert outs[0] == outs[1], (w, h, dw, dh)
