@@ -45,7 +45,9 @@ def main():
             tex.append(R.Texture(7, 6, True, np.random.RandomState(5).rand(6, 7, 4).tobytes(), is_uint8=False))
             tex.append(R.Texture.from_numpy(np.random.RandomState(8).randint(0, 256, (12, 10, 3)).astype(np.uint8)))
             streams.stream_extensions(ctx, tex, seed, n=80)
-            got.append((ctx.get_buffer_as_yuv420p().tobytes(), cases.digest(ctx)))
+            rs = np.random.RandomState(seed)   # present path incl. the scaling branch: same planes at a random other size
+            dw, dh = int(rs.randint(2, 2 * w)), int(rs.randint(2, 2 * h))
+            got.append((ctx.get_buffer_as_yuv420p().tobytes(), ctx.get_buffer_as_yuv420p_scaled(dw, dh).tobytes(), cases.digest(ctx)))
         if got[0] != got[1]:
             bad.append(("ext/port", seed))
         if (seed - first) % 100 == 99:
