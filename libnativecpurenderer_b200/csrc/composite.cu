@@ -31,6 +31,9 @@ __device__ __noinline__ double ncr_sqrt(double a) { return __dsqrt_rn(a); }
 #define DIV(a, b) ncr_div((a), (b))
 
 #define FULL 0xffffffffu
+#ifndef NCR_USE_COVERS
+#define NCR_USE_COVERS 1   // 0: ignore the entries' "box contains the region" bit (A/B builds)
+#endif
 // u8 -> k/255.0 table: one private copy per lane (32 copies, entries 256 B apart), so a lookup is conflict-free and its
 // shared address is a single byte permute of (texel, lane*8): byte 1 <- texel byte, byte 0 <- lane*8.
 #define NCR_LUT_COPIES 32
@@ -442,18 +445,23 @@ template <bool ALPHA, bool COUNT>
 __device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A, const Slots& S,
                                           const double* lut, uint32_t lut_base /* lane * 8 */,
                                           double (&dr)[NCR_P], double (&dg)[NCR_P], double (&db)[NCR_P], double (&da)[NCR_P],
-                                          unsigned long long& n_applied) {
+                                          unsigned long long& n_applied, const bool covers /* warp-uniform: box contains the region */) {
     const uint32_t op = c.op, flags = c.flags;
     // pixel-box membership: the reference's loop bounds (boxes are clamped to the canvas on the host, so a pixel slot
     // outside the canvas is never inside a box).  (unsigned)(v - lo) < (unsigned)(hi - lo)  <=>  lo <= v < hi.
-    const unsigned wx = (unsigned)(c.r - c.l), wy = (unsigned)(c.b - c.t);
-    bool inx[NCR_NX], iny[NCR_NY];
-#pragma unroll
-    for (int k = 0; k < NCR_NX; ++k) inx[k] = (unsigned)(S.xs[k] - c.l) < wx;
-#pragma unroll
-    for (int k = 0; k < NCR_NY; ++k) iny[k] = (unsigned)(S.ys[k] - c.t) < wy;
+    // ncr_bin_fine tags the entry when the box contains the whole region (the usual case at the slanted edge of a rotated quad,
+    // whose bounding box is larger than the quad): every slot is inside, the tests are skipped.
     bool in[NCR_P];
-    FOR4 in[p] = inx[SX(p)] && iny[SY(p)];
+    FOR4 in[p] = true;
+    if (!covers) {
+        const unsigned wx = (unsigned)(c.r - c.l), wy = (unsigned)(c.b - c.t);
+        bool inx[NCR_NX], iny[NCR_NY];
+#pragma unroll
+        for (int k = 0; k < NCR_NX; ++k) inx[k] = (unsigned)(S.xs[k] - c.l) < wx;
+#pragma unroll
+        for (int k = 0; k < NCR_NY; ++k) iny[k] = (unsigned)(S.ys[k] - c.t) < wy;
+        FOR4 in[p] = inx[SX(p)] && iny[SY(p)];
+    }
 
     if (flags & NCR_F_FAST_AFFINE) {   // DrawTexture / DrawSplittedTexture on RGBA8, nearest: the hot case, tested first
         tex_fast<ALPHA, COUNT, false>(c, op, flags, S, lut, lut_base, in, dr, dg, db, da, n_applied);
@@ -718,34 +726,43 @@ __device__ __forceinline__ bool run_region(const NcrFlushArgs& A, NcrCmd (*s_cmd
     if (lcount != 0 && !have_cmd0) stage_cmd(A, &s_cmd[0][slot], cur, lane);
     bool staged_next = false;
     if (lcount == 0 && next_valid) { stage_cmd(A, &s_cmd[0][slot], __shfl_sync(FULL, next_ents, 0), lane); staged_next = true; }
-    for (uint32_t k = 0; k < lcount; ++k) {
-        const bool more = k + 1 < lcount;
-        uint32_t nxt = 0;
-        if (more) {
-            if (((k + 1) & 31u) == 0u) ents = (k + 1 + lane < lcount) ? __ldg(list + loff + k + 1 + lane) : 0u;   // next 32 entries
-            nxt = __shfl_sync(FULL, ents, (k + 1) & 31);
-        } else if (next_valid) {
-            nxt = __shfl_sync(FULL, next_ents, 0);
-        }
-        const bool fetch = more || next_valid;
-        uint4 pre = make_uint4(0, 0, 0, 0);
-        if (fetch && lane < (int)WORDS) pre = __ldg((const uint4*)(A.cmds + (nxt & NCR_ENTRY_INDEX)) + lane);   // in flight during the apply
-        const NcrCmd& c = s_cmd[0][slot];
+    // Every lane takes part in staging (lanes 15..31 repeat the last 16-byte word: same value to the same address), so the fetch and
+    // the store carry no predicate.  The list is walked 32 entries at a time: the next chunk's entries (at the end of the list, the
+    // next region's first entries in the prefetch variant) are loaded at the top of a chunk and first touched at its last command, so
+    // the inner loop holds no list address and no refill test.  Past the end of everything the "next command" is entry 0 of the
+    // current chunk — a valid command index whose copy is staged and never run.
+    const uint32_t cmd_word = min(lane, (int)WORDS - 1);
+    const uint4* const cmd_words = (const uint4*)A.cmds + cmd_word;    // + 15 * index: this lane's word of command `index`
+    NcrCmd* c_cur = &s_cmd[0][slot];
+    NcrCmd* c_nxt = &s_cmd[0][slot ^ 1];
+    for (uint32_t base = 0; base < lcount; base += 32) {
+        const uint32_t n_here = min(32u, lcount - base);
+        uint32_t ents_n = ents;
+        if (base + 32 < lcount) ents_n = (base + 32 + lane < lcount) ? __ldg(list + loff + base + 32 + lane) : 0u;
+        else if (next_valid) ents_n = next_ents;
+        for (uint32_t i = 1; i <= n_here; ++i) {
+            uint32_t nxt = __shfl_sync(FULL, ents, i);            // command i of this chunk (source lane is taken modulo 32)
+            if (i == n_here) nxt = __shfl_sync(FULL, ents_n, 0);   // last one of the chunk: the next chunk's / region's first
+            const uint4 pre = __ldg(cmd_words + (size_t)(nxt & NCR_ENTRY_INDEX) * WORDS);   // in flight during the apply
+            const NcrCmd& c = *c_cur;
 #ifdef NCR_TMA_IDENT
-        if (tbox && cur == ((uint32_t)A.tma_cmd | NCR_ENTRY_INTERIOR)) {   // the staged box belongs to this command
-            tma_wait(tbox_mbar, tbox_parity);
-            *tbox_used = true;
-            apply_interior<ALPHA, COUNT>(c, S, lut, lut_base, dr, dg, db, da, n_applied, tbox, ly * NCR_RW + lx);
-        } else
+            if (tbox && cur == ((uint32_t)A.tma_cmd | NCR_ENTRY_INTERIOR | NCR_ENTRY_COVERS)) {   // the staged box belongs to this command
+                tma_wait(tbox_mbar, tbox_parity);
+                *tbox_used = true;
+                apply_interior<ALPHA, COUNT>(c, S, lut, lut_base, dr, dg, db, da, n_applied, tbox, ly * NCR_RW + lx);
+            } else
 #endif
-        if (!(cur & NCR_ENTRY_INTERIOR) || !apply_interior<ALPHA, COUNT>(c, S, lut, lut_base, dr, dg, db, da, n_applied))
-            apply_cmd<ALPHA, COUNT>(c, A, S, lut, lut_base, dr, dg, db, da, n_applied);
-        if (fetch && lane < (int)WORDS) ((uint4*)&s_cmd[0][slot ^ 1])[lane] = pre;
-        __syncwarp();
-        if (fetch) slot ^= 1;
-        if (!more) staged_next = next_valid;
-        cur = nxt;
+            if (!(cur & NCR_ENTRY_INTERIOR) || !apply_interior<ALPHA, COUNT>(c, S, lut, lut_base, dr, dg, db, da, n_applied))
+                apply_cmd<ALPHA, COUNT>(c, A, S, lut, lut_base, dr, dg, db, da, n_applied, NCR_USE_COVERS && (cur & NCR_ENTRY_COVERS) != 0);
+            ((uint4*)c_nxt)[cmd_word] = pre;
+            __syncwarp();
+            NcrCmd* const t = c_cur; c_cur = c_nxt; c_nxt = t;
+            cur = nxt;
+        }
+        ents = ents_n;
     }
+    slot = (int)(c_cur - &s_cmd[0][0]);
+    if (lcount != 0) staged_next = next_valid;
 
     // region write-back: canonical f64 canvas (only if something was drawn, and not for a present-only flush) and the fused (iu8)(v*255) image
 #ifdef NCR_ROW4

@@ -185,12 +185,12 @@ __global__ void __launch_bounds__(256, NCR_FINE_MIN_CTAS) ncr_bin_fine(NcrFlushA
             for (int u = 0; u < NCR_FINE_U; ++u) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const uint32_t cd = (code[u] >> (2 * h)) & 3u;
+                    const uint32_t cd = (code[u] >> (3 * h)) & 3u, cov = (code[u] >> (3 * h + 2)) & 1u;
                     const uint32_t m = __ballot_sync(0xffffffffu, cd != 0u);
                     n_interior += (pass == 0 && cd == 2u) ? 1u : 0u;   // per lane; reduced once per tile (statistics)
                     if (cd) {
                         const uint32_t at = pos[h] + __popc(m & lt);
-                        const uint32_t e = idx[u] | (cd == 2u ? NCR_ENTRY_INTERIOR : 0u);
+                        const uint32_t e = idx[u] | (cd == 2u ? NCR_ENTRY_INTERIOR : 0u) | (cov ? NCR_ENTRY_COVERS : 0u);
                         if (pass == 0) { if (at < NCR_FINE_STAGE) s_stage[warp][h][at] = e; }
                         else A.fine_list[off[h] + at] = e;
                     }

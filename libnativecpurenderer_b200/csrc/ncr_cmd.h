@@ -73,7 +73,8 @@ struct alignas(16) NcrBox {
 #define NCR_REGION_H 8
 #define NCR_REGIONS_PER_TILE 2
 #define NCR_ENTRY_INTERIOR 0x80000000u
-#define NCR_ENTRY_INDEX 0x7fffffffu
+#define NCR_ENTRY_COVERS 0x40000000u   // the command's pixel box contains the whole region (no box-membership test per pixel); set with INTERIOR too
+#define NCR_ENTRY_INDEX 0x3fffffffu
 
 struct NcrFrameDims {
     int32_t w, h, ipp;

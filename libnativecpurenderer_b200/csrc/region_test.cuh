@@ -40,7 +40,8 @@ __device__ __forceinline__ NcrQuadRange ncr_quad_range(const double2 m01, const 
 }
 
 // Classifies command `c` (pixel box `box` = l, r, t, b) against BOTH regions of the tile whose top-left pixel is (x0, y0):
-// returns code(top) | code(bottom) << 2.  The caller has already established that the box intersects the tile.
+// returns, per region (top in bits 0..2, bottom in bits 3..5), code | covers << 2 where `covers` = the box contains the whole region.
+// The caller has already established that the box intersects the tile.
 __device__ __forceinline__ uint32_t ncr_region_codes(const NcrCmd* __restrict__ c, const int4 box, int x0, int y0) {
     uint32_t hit[2], covers[2];
 #pragma unroll
@@ -81,5 +82,5 @@ __device__ __forceinline__ uint32_t ncr_region_codes(const NcrCmd* __restrict__ 
             else if (covers[h] && q.x_min >= lo.x && q.x_max <= hi.x && q.y_min >= lo.y && q.y_max <= hi.y) code[h] = 2u;
         }
     }
-    return code[0] | (code[1] << 2);
+    return (code[0] | (code[0] ? covers[0] << 2 : 0u)) | ((code[1] | (code[1] ? covers[1] << 2 : 0u)) << 3);
 }
