@@ -733,18 +733,17 @@ __device__ __forceinline__ bool run_region(const NcrFlushArgs& A, NcrCmd (*s_cmd
     // current chunk — a valid command index whose copy is staged and never run.
     const uint32_t cmd_word = min(lane, (int)WORDS - 1);
     const uint4* const cmd_words = (const uint4*)A.cmds + cmd_word;    // + 15 * index: this lane's word of command `index`
-    NcrCmd* c_cur = &s_cmd[0][slot];
-    NcrCmd* c_nxt = &s_cmd[0][slot ^ 1];
     for (uint32_t base = 0; base < lcount; base += 32) {
         const uint32_t n_here = min(32u, lcount - base);
         uint32_t ents_n = ents;
         if (base + 32 < lcount) ents_n = (base + 32 + lane < lcount) ? __ldg(list + loff + base + 32 + lane) : 0u;
         else if (next_valid) ents_n = next_ents;
         for (uint32_t i = 1; i <= n_here; ++i) {
-            uint32_t nxt = __shfl_sync(FULL, ents, i);            // command i of this chunk (source lane is taken modulo 32)
-            if (i == n_here) nxt = __shfl_sync(FULL, ents_n, 0);   // last one of the chunk: the next chunk's / region's first
+            // command i of this chunk (source lane is taken modulo 32); after the chunk's last one: the next chunk's / region's first
+            const bool last = i == n_here;
+            const uint32_t nxt = __shfl_sync(FULL, last ? ents_n : ents, last ? 0u : i);
             const uint4 pre = __ldg(cmd_words + (size_t)(nxt & NCR_ENTRY_INDEX) * WORDS);   // in flight during the apply
-            const NcrCmd& c = *c_cur;
+            const NcrCmd& c = s_cmd[0][slot];
 #ifdef NCR_TMA_IDENT
             if (tbox && cur == ((uint32_t)A.tma_cmd | NCR_ENTRY_INTERIOR | NCR_ENTRY_COVERS)) {   // the staged box belongs to this command
                 tma_wait(tbox_mbar, tbox_parity);
@@ -754,14 +753,13 @@ __device__ __forceinline__ bool run_region(const NcrFlushArgs& A, NcrCmd (*s_cmd
 #endif
             if (!(cur & NCR_ENTRY_INTERIOR) || !apply_interior<ALPHA, COUNT>(c, S, lut, lut_base, dr, dg, db, da, n_applied))
                 apply_cmd<ALPHA, COUNT>(c, A, S, lut, lut_base, dr, dg, db, da, n_applied, NCR_USE_COVERS && (cur & NCR_ENTRY_COVERS) != 0);
-            ((uint4*)c_nxt)[cmd_word] = pre;
+            slot ^= 1;
+            ((uint4*)&s_cmd[0][slot])[cmd_word] = pre;
             __syncwarp();
-            NcrCmd* const t = c_cur; c_cur = c_nxt; c_nxt = t;
             cur = nxt;
         }
         ents = ents_n;
     }
-    slot = (int)(c_cur - &s_cmd[0][0]);
     if (lcount != 0) staged_next = next_valid;
 
     // region write-back: canonical f64 canvas (only if something was drawn, and not for a present-only flush) and the fused (iu8)(v*255) image
