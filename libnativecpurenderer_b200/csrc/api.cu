@@ -254,7 +254,6 @@ struct NcrContext {
     DevVec<uint32_t> d_binbox;
     DevVec<double> d_aux;
     DevVec<uint32_t> d_coarse, d_coarse_off, d_fine, d_fine_off, d_cursors;
-    DevVec<NcrBox> d_coarse_boxes;
     DevVec<unsigned char> d_u8;
     DevVec<unsigned char> d_yuv;
     bool u8_valid = false;
@@ -511,7 +510,7 @@ bool flush(NcrContext* c, bool want_u8, bool want_yuv = false) {
     const size_t n_regions = n_tiles * NCR_REGIONS_PER_TILE;
     NcrStaging& S = c->stg[c->cur];
     bool ok = c->d_cmds.reserve(c->n) && c->d_boxes.reserve(c->n) && c->d_binbox.reserve(c->n) && c->d_aux.reserve(c->n_aux + 2) &&
-              c->d_coarse.reserve(c->coarse_need + 1) && c->d_coarse_boxes.reserve(c->coarse_need + 1) && c->d_coarse_off.reserve(2 * n_bins) &&
+              c->d_coarse.reserve(c->coarse_need + 1) && c->d_coarse_off.reserve(2 * n_bins) &&
               c->d_fine.reserve(c->fine_need + 1) && c->d_fine_off.reserve(2 * n_regions) && c->d_cursors.reserve(8);
     if (ok && (want_u8 || want_yuv)) ok = c->d_u8.reserve(n_elems);   // the YUV planes are converted from the u8 image
     if (ok && want_yuv) ok = c->d_yuv.reserve(yuv_bytes_of(c));
@@ -537,12 +536,11 @@ bool flush(NcrContext* c, bool want_u8, bool want_yuv = false) {
     A.n_cmds = (uint32_t)c->n;
     A.load_fb = c->load_fb ? 1u : 0u;
     A.coarse_list = c->n <= kDirectBinMaxCmds ? nullptr : c->d_coarse.p;
-    A.coarse_boxes = c->d_coarse_boxes.p;
     A.coarse_off = c->d_coarse_off.p;
     A.fine_list = c->d_fine.p;
     A.fine_off = c->d_fine_off.p;
     A.cursors = c->d_cursors.p;
-    A.coarse_cap = (uint32_t)std::min(c->d_coarse.cap, c->d_coarse_boxes.cap);
+    A.coarse_cap = (uint32_t)c->d_coarse.cap;
     A.fine_cap = (uint32_t)c->d_fine.cap;
     A.tma_map = c->tma_map; A.tma_cmd = c->tma_cmd; A.tma_x = c->tma_x; A.tma_y = c->tma_y; A.tma_w = c->tma_w; A.tma_h = c->tma_h;
     c->tma_map = nullptr; c->tma_cmd = -1;
@@ -879,7 +877,7 @@ void DestroyRenderContext(RenderContext* ctx) {
     c->refs.clear();
     c->last_refs.clear();
     c->d_cmds.release(); c->d_boxes.release(); c->d_binbox.release(); c->d_aux.release();
-    c->d_coarse.release(); c->d_coarse_boxes.release(); c->d_coarse_off.release(); c->d_fine.release(); c->d_fine_off.release();
+    c->d_coarse.release(); c->d_coarse_off.release(); c->d_fine.release(); c->d_fine_off.release();
     c->d_cursors.release(); c->d_u8.release(); c->d_yuv.release();
     c->d_sws_tables.release(); c->d_sws_mid.release(); c->d_sws_out.release();
     for (int k = 0; k < 2; ++k) {

@@ -109,11 +109,7 @@ __global__ void __launch_bounds__(32 * NCR_COARSE_WARPS) ncr_bin_coarse(NcrFlush
         if (count == 0) return;
         for (uint32_t base = beg; base < end; base += 32) {   // replay: one mask word per 32 commands
             const uint32_t m = my_masks[(base - beg) / 32];
-            if (m >> lane & 1u) {
-                const uint32_t at = pos + __popc(m & ((1u << lane) - 1));
-                A.coarse_list[at] = base + lane;
-                A.coarse_boxes[at] = A.boxes[base + lane];
-            }
+            if (m >> lane & 1u) A.coarse_list[pos + __popc(m & ((1u << lane) - 1))] = base + lane;
             pos += __popc(m);
         }
         return;
@@ -129,11 +125,7 @@ __global__ void __launch_bounds__(32 * NCR_COARSE_WARPS) ncr_bin_coarse(NcrFlush
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint32_t m = __ballot_sync(0xffffffffu, hit[k]);
-            if (hit[k]) {
-                const uint32_t at = pos + __popc(m & ((1u << lane) - 1));
-                A.coarse_list[at] = base + k * 32 + lane;
-                A.coarse_boxes[at] = A.boxes[base + k * 32 + lane];
-            }
+            if (hit[k]) A.coarse_list[pos + __popc(m & ((1u << lane) - 1))] = base + k * 32 + lane;
             pos += __popc(m);
         }
     }
@@ -182,10 +174,7 @@ __global__ void __launch_bounds__(256, NCR_FINE_MIN_CTAS) ncr_bin_fine(NcrFlushA
                 idx[u] = direct ? at : A.coarse_list[cbase + at];
             }
 #pragma unroll
-            for (int u = 0; u < NCR_FINE_U; ++u) {   // the bin list carries each entry's box next to its index: no gather through idx
-                const uint32_t at = min(k + u * 32 + lane, ccount - 1);
-                bxs[u] = direct ? __ldg((const int4*)&A.boxes[at]) : __ldg((const int4*)&A.coarse_boxes[cbase + at]);
-            }
+            for (int u = 0; u < NCR_FINE_U; ++u) bxs[u] = __ldg((const int4*)&A.boxes[idx[u]]);
 #pragma unroll
             for (int u = 0; u < NCR_FINE_U; ++u) {
                 const bool in_tile = bxs[u].x < bxs[u].y && bxs[u].z < bxs[u].w && bxs[u].x < x1 && bxs[u].y > x0 && bxs[u].z < y1 &&

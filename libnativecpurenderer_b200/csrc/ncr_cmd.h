@@ -95,8 +95,6 @@ struct NcrFlushArgs {
     uint32_t n_cmds;
     uint32_t load_fb;           // 0: every tile's list starts with SET_COLOR, do not read fb
     uint32_t* coarse_list;      // capacity coarse_cap; nullptr: small batch — ncr_bin_coarse is skipped and ncr_bin_fine scans the commands directly
-    NcrBox* coarse_boxes;       // capacity coarse_cap: the pixel box of every bin-list entry, so that ncr_bin_fine reads boxes coalesced
-                                // instead of gathering them through the command index (one dependent load less per candidate)
     uint32_t* coarse_off;       // [bins] offset, [bins] count
     uint32_t* fine_list;        // capacity fine_cap; entries: command index | NCR_ENTRY_INTERIOR
     uint32_t* fine_off;         // per region: {offset, count} (uint2[regions])
