@@ -19,6 +19,7 @@
 // IEEE operations on the same operands, evaluated once.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #include "kernels.h"
 #include "ncr_cmd.h"
 #include "pixel_math.cuh"
@@ -325,40 +326,40 @@ __device__ __forceinline__ void tex_fast(const NcrCmd& c, const uint32_t op, con
 #pragma unroll
     for (int k = 0; k < NCR_NY; ++k) { ay[k] = MUL(i2, S.fy[k]); by[k] = MUL(i3, S.fy[k]); }
     const double cx = c.x, cy = c.y, cxw = c.xw, cyh = c.yh, sx = c.sx, sy = c.sy;
-    double u[NCR_P], v[NCR_P];
-    FOR4 {
-        const double X = ADD(ADD(ax[SX(p)], ay[SY(p)]), i4);
-        const double Y = ADD(ADD(bx[SX(p)], by[SY(p)]), i5);
-        // the four inclusive bounds, cpp:765-768 (NaN compares false on both sides, as in C)
-        if (!INTERIOR) in[p] = in[p] && !(X < cx) && !(X > cxw) && !(Y < cy) && !(Y > cyh);
-        u[p] = MUL(SUB(X, cx), sx);   // cpp:770-771
-        v[p] = MUL(SUB(Y, cy), sy);
-    }
-    if (!INTERIOR && !__any_sync(FULL, any_slot(in))) return;
-    if (op == NCR_OP_TEX_SPLIT) {
-        // cpp:812-813: u = (uStart + (uEnd - uStart) * u / tex->width) * tex->width
-        const double uS = c.p[0], dU = c.p[1], vS = c.p[2], dV = c.p[3], fw = c.p[4], fh = c.p[5];
-        // the hot path only takes power-of-two textures here (the recorder routes the others to the general path):
-        // x / 2^k and x * 2^-k are the same correctly rounded value
-        const double rw = c.p[6], rh = c.p[7];
-        FOR4 {
-            u[p] = MUL(ADD(uS, MUL(MUL(dU, u[p]), rw)), fw);
-            v[p] = MUL(ADD(vS, MUL(MUL(dV, v[p]), rh)), fh);
-        }
-    }
-    // InterpolateColorFromBuffer, cpp:560-566: clamp u<0 -> 0, u >= w-1 -> w-2, then (i64) truncation.  Done after the
-    // truncation here, which is the same function: trunc(u) <= 0 iff u < 1, and because w-1 is an integer,
-    // u >= w-1 iff trunc(u) >= w-1 (cvt.rzi saturates, so huge u stays >= w-1).
     const int tw = c.tex_w, tw2 = tw - 2, th2 = c.tex_h - 2;
     const uint32_t* t32 = (const uint32_t*)c.tex;
+    // cpp:812-813: u = (uStart + (uEnd - uStart) * u / tex->width) * tex->width.  The hot path only takes power-of-two textures
+    // here (the recorder routes the others to the general path): x / 2^k and x * 2^-k are the same correctly rounded value.
+    const double uS = c.p[0], dU = c.p[1], vS = c.p[2], dV = c.p[3], fw = c.p[4], fh = c.p[5], rw = c.p[6], rh = c.p[7];
     uint32_t tx[NCR_P];
-    FOR4 {
-        // x >= w-1 ? w-2 : x is min(x, w-2) on integers; max(.., 0) also keeps 1-texel-wide textures in bounds (the
-        // reference reads out of bounds there).  min + relu is one VIMNMX.
-        const int xi = __vimin_s32_relu(__double2int_rz(u[p]), tw2);
-        const int yi = __vimin_s32_relu(__double2int_rz(v[p]), th2);
-        tx[p] = (INTERIOR || in[p]) ? __ldg(t32 + (yi * tw + xi)) : 0u;
-    }
+    // Each slot is mapped, clamped and fetched in one go (no u[] / v[] arrays live across the slots).  The split remap is a
+    // compile-time variant of the slot loop, chosen by one warp-uniform branch: with the test inside the loop ptxas predicates the
+    // eight remap instructions of every slot, which non-split draws then issue for nothing (profiles/README.md, r2 session 3).
+    // InterpolateColorFromBuffer, cpp:560-566: clamp u<0 -> 0, u >= w-1 -> w-2, then (i64) truncation.  Done after the
+    // truncation here, which is the same function: trunc(u) <= 0 iff u < 1, and because w-1 is an integer,
+    // u >= w-1 iff trunc(u) >= w-1 (cvt.rzi saturates, so huge u stays >= w-1).  x >= w-1 ? w-2 : x is min(x, w-2) on
+    // integers; max(.., 0) also keeps 1-texel-wide textures in bounds (the reference reads out of bounds there).
+    auto map_and_fetch = [&](auto split_c) {
+        constexpr bool SPLIT = decltype(split_c)::value;
+        FOR4 {
+            const double X = ADD(ADD(ax[SX(p)], ay[SY(p)]), i4);
+            const double Y = ADD(ADD(bx[SX(p)], by[SY(p)]), i5);
+            // the four inclusive bounds, cpp:765-768 (NaN compares false on both sides, as in C)
+            if (!INTERIOR) in[p] = in[p] && !(X < cx) && !(X > cxw) && !(Y < cy) && !(Y > cyh);
+            double u = MUL(SUB(X, cx), sx);   // cpp:770-771
+            double v = MUL(SUB(Y, cy), sy);
+            if (SPLIT) {
+                u = MUL(ADD(uS, MUL(MUL(dU, u), rw)), fw);
+                v = MUL(ADD(vS, MUL(MUL(dV, v), rh)), fh);
+            }
+            const int xi = __vimin_s32_relu(__double2int_rz(u), tw2);
+            const int yi = __vimin_s32_relu(__double2int_rz(v), th2);
+            tx[p] = (INTERIOR || in[p]) ? __ldg(t32 + (yi * tw + xi)) : 0u;
+        }
+    };
+    if (op == NCR_OP_TEX_SPLIT) map_and_fetch(std::true_type{});
+    else map_and_fetch(std::false_type{});
+    if (!INTERIOR && !__any_sync(FULL, any_slot(in))) return;
     if ((flags & (NCR_F_CT_RGB_ONE | NCR_F_ALPHA_LT1)) == (NCR_F_CT_RGB_ONE | NCR_F_ALPHA_LT1))
         shade_rgba8<ALPHA, COUNT, true, true>(c, lut_base, tx, in, dr, dg, db, da, n_applied);
     else if (flags & NCR_F_CT_RGB_ONE) shade_rgba8<ALPHA, COUNT, true>(c, lut_base, tx, in, dr, dg, db, da, n_applied);
