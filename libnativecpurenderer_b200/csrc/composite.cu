@@ -314,7 +314,7 @@ __device__ __forceinline__ void shade_bilinear_rgba8(const NcrCmd& c, uint32_t l
 // INTERIOR: ncr_bin_fine proved that every pixel of the region passes the box and the four bounds: `in` is constant true, the
 // bounds are not evaluated and every select on coverage folds away.
 template <bool ALPHA, bool COUNT, bool INTERIOR>
-__device__ __forceinline__ void tex_fast(const NcrCmd& c, const uint32_t op, const uint32_t flags, const Slots& S,
+__device__ __forceinline__ void tex_fast(const NcrCmd& c, const uint32_t hint /* the list entry's NCR_ENTRY_* bits */, const Slots& S,
                                          const double* lut, uint32_t lut_base, bool (&in)[NCR_P], double (&dr)[NCR_P], double (&dg)[NCR_P],
                                          double (&db)[NCR_P], double (&da)[NCR_P], unsigned long long& n_applied) {
     // TransformPointFromMatrix(inv, i, j), cpp:451-452: (inv0*i + inv2*j) + inv4.  inv0*i depends only on the pixel
@@ -357,12 +357,12 @@ __device__ __forceinline__ void tex_fast(const NcrCmd& c, const uint32_t op, con
             tx[p] = (INTERIOR || in[p]) ? __ldg(t32 + (yi * tw + xi)) : 0u;
         }
     };
-    if (op == NCR_OP_TEX_SPLIT) map_and_fetch(std::true_type{});
+    if (hint & NCR_ENTRY_SPLIT) map_and_fetch(std::true_type{});
     else map_and_fetch(std::false_type{});
     if (!INTERIOR && !__any_sync(FULL, any_slot(in))) return;
-    if ((flags & (NCR_F_CT_RGB_ONE | NCR_F_ALPHA_LT1)) == (NCR_F_CT_RGB_ONE | NCR_F_ALPHA_LT1))
+    if ((hint & (NCR_ENTRY_RGB_ONE | NCR_ENTRY_ALPHA_LT1)) == (NCR_ENTRY_RGB_ONE | NCR_ENTRY_ALPHA_LT1))
         shade_rgba8<ALPHA, COUNT, true, true>(c, lut_base, tx, in, dr, dg, db, da, n_applied);
-    else if (flags & NCR_F_CT_RGB_ONE) shade_rgba8<ALPHA, COUNT, true>(c, lut_base, tx, in, dr, dg, db, da, n_applied);
+    else if (hint & NCR_ENTRY_RGB_ONE) shade_rgba8<ALPHA, COUNT, true>(c, lut_base, tx, in, dr, dg, db, da, n_applied);
     else shade_rgba8<ALPHA, COUNT, false>(c, lut_base, tx, in, dr, dg, db, da, n_applied);
 }
 
@@ -371,16 +371,18 @@ __device__ __forceinline__ void tex_fast(const NcrCmd& c, const uint32_t op, con
 // same as in apply_cmd — only `in` is the constant true).  Returns false (warp-uniform) for ops that have no interior
 // variant; the caller then runs apply_cmd, which is always correct.
 template <bool ALPHA, bool COUNT>
-__device__ __forceinline__ bool apply_interior(const NcrCmd& c, const Slots& S, const double* lut, uint32_t lut_base,
+__device__ __forceinline__ bool apply_interior(const NcrCmd& c, const uint32_t hint, const Slots& S, const double* lut, uint32_t lut_base,
                                                double (&dr)[NCR_P], double (&dg)[NCR_P], double (&db)[NCR_P], double (&da)[NCR_P],
                                                unsigned long long& n_applied, const uint32_t* tbox = nullptr, int tbox_at = 0) {
-    const uint32_t op = c.op, flags = c.flags;
     bool in[NCR_P];
     FOR4 in[p] = true;
-    if (flags & NCR_F_FAST_AFFINE) {
-        tex_fast<ALPHA, COUNT, true>(c, op, flags, S, lut, lut_base, in, dr, dg, db, da, n_applied);
+    // The hot case is chosen from the list entry (a register), not from the staged command: its parameter loads do not wait for
+    // the flag word's shared-memory round trip.
+    if (hint & NCR_ENTRY_FAST_AFFINE) {
+        tex_fast<ALPHA, COUNT, true>(c, hint, S, lut, lut_base, in, dr, dg, db, da, n_applied);
         return true;
     }
+    const uint32_t op = c.op, flags = c.flags;
     if (op == NCR_OP_FILL_COLOR || op == NCR_OP_RECT) {   // constant colour, see apply_cmd
         const double sa = c.p[3];
         if (sa != 1.0) {
@@ -446,8 +448,8 @@ template <bool ALPHA, bool COUNT>
 __device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A, const Slots& S,
                                           const double* lut, uint32_t lut_base /* lane * 8 */,
                                           double (&dr)[NCR_P], double (&dg)[NCR_P], double (&db)[NCR_P], double (&da)[NCR_P],
-                                          unsigned long long& n_applied, const bool covers /* warp-uniform: box contains the region */) {
-    const uint32_t op = c.op, flags = c.flags;
+                                          unsigned long long& n_applied, const bool covers /* warp-uniform: box contains the region */,
+                                          const uint32_t hint /* the list entry's NCR_ENTRY_* bits */) {
     // pixel-box membership: the reference's loop bounds (boxes are clamped to the canvas on the host, so a pixel slot
     // outside the canvas is never inside a box).  (unsigned)(v - lo) < (unsigned)(hi - lo)  <=>  lo <= v < hi.
     // ncr_bin_fine tags the entry when the box contains the whole region (the usual case at the slanted edge of a rotated quad,
@@ -464,10 +466,11 @@ __device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A
         FOR4 in[p] = inx[SX(p)] && iny[SY(p)];
     }
 
-    if (flags & NCR_F_FAST_AFFINE) {   // DrawTexture / DrawSplittedTexture on RGBA8, nearest: the hot case, tested first
-        tex_fast<ALPHA, COUNT, false>(c, op, flags, S, lut, lut_base, in, dr, dg, db, da, n_applied);
+    if (hint & NCR_ENTRY_FAST_AFFINE) {   // DrawTexture / DrawSplittedTexture on RGBA8, nearest: the hot case, tested first
+        tex_fast<ALPHA, COUNT, false>(c, hint, S, lut, lut_base, in, dr, dg, db, da, n_applied);
         return;
     }
+    const uint32_t op = c.op, flags = c.flags;
 
     if (op == NCR_OP_SET_COLOR) {   // cpp:643-657
         FOR4 if (in[p]) {
@@ -746,14 +749,14 @@ __device__ __forceinline__ bool run_region(const NcrFlushArgs& A, NcrCmd (*s_cmd
             const uint4 pre = __ldg(cmd_words + (size_t)(nxt & NCR_ENTRY_INDEX) * WORDS);   // in flight during the apply
             const NcrCmd& c = s_cmd[0][slot];
 #ifdef NCR_TMA_IDENT
-            if (tbox && cur == ((uint32_t)A.tma_cmd | NCR_ENTRY_INTERIOR | NCR_ENTRY_COVERS)) {   // the staged box belongs to this command
+            if (tbox && (cur & ~NCR_ENTRY_HINTS) == ((uint32_t)A.tma_cmd | NCR_ENTRY_INTERIOR | NCR_ENTRY_COVERS)) {   // the staged box belongs to this command
                 tma_wait(tbox_mbar, tbox_parity);
                 *tbox_used = true;
-                apply_interior<ALPHA, COUNT>(c, S, lut, lut_base, dr, dg, db, da, n_applied, tbox, ly * NCR_RW + lx);
+                apply_interior<ALPHA, COUNT>(c, cur, S, lut, lut_base, dr, dg, db, da, n_applied, tbox, ly * NCR_RW + lx);
             } else
 #endif
-            if (!(cur & NCR_ENTRY_INTERIOR) || !apply_interior<ALPHA, COUNT>(c, S, lut, lut_base, dr, dg, db, da, n_applied))
-                apply_cmd<ALPHA, COUNT>(c, A, S, lut, lut_base, dr, dg, db, da, n_applied, NCR_USE_COVERS && (cur & NCR_ENTRY_COVERS) != 0);
+            if (!(cur & NCR_ENTRY_INTERIOR) || !apply_interior<ALPHA, COUNT>(c, cur, S, lut, lut_base, dr, dg, db, da, n_applied))
+                apply_cmd<ALPHA, COUNT>(c, A, S, lut, lut_base, dr, dg, db, da, n_applied, NCR_USE_COVERS && (cur & NCR_ENTRY_COVERS) != 0, cur);
             slot ^= 1;
             ((uint4*)&s_cmd[0][slot])[cmd_word] = pre;
             __syncwarp();

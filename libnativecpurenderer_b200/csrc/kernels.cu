@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(32 * NCR_FINE_WARPS, NCR_FINE_MIN_CTAS) ncr_bi
                     n_interior += (pass == 0 && cd == 2u) ? 1u : 0u;   // per lane; reduced once per tile (statistics)
                     if (cd) {
                         const uint32_t at = pos[h] + __popc(m & lt);
-                        const uint32_t e = idx[u] | (cd == 2u ? NCR_ENTRY_INTERIOR : 0u) | (cov ? NCR_ENTRY_COVERS : 0u);
+                        const uint32_t e = idx[u] | (cd == 2u ? NCR_ENTRY_INTERIOR : 0u) | (cov ? NCR_ENTRY_COVERS : 0u) | (code[u] & NCR_ENTRY_HINTS);
                         if (pass == 0) { if (at < NCR_FINE_STAGE) s_stage[warp][h][at] = e; }
                         else A.fine_list[off[h] + at] = e;
                     }

@@ -67,14 +67,21 @@ struct alignas(16) NcrBox {
 #define NCR_TILE 16            // binning tile edge in pixels
 #define NCR_COARSE 8           // coarse bin edge in tiles (128 px)
 // The composite's work unit is a REGION: the top or bottom 16x8-px half of a tile (region = 2 * tile + half).  ncr_bin_fine
-// writes one ordered command list per region.  A list entry is a command index; bit 31 marks the command as INTERIOR to
+// writes one ordered command list per region.  A list entry is a command index plus tag bits; bit 31 marks the command as INTERIOR to
 // the region: every pixel of the region provably passes the command's box and coverage tests (see region_code()).
 #define NCR_REGION_W 16
 #define NCR_REGION_H 8
 #define NCR_REGIONS_PER_TILE 2
 #define NCR_ENTRY_INTERIOR 0x80000000u
 #define NCR_ENTRY_COVERS 0x40000000u   // the command's pixel box contains the whole region (no box-membership test per pixel); set with INTERIOR too
-#define NCR_ENTRY_INDEX 0x3fffffffu
+// Dispatch hints, copied by ncr_bin_fine from the command's op / flags (it reads them anyway): the composite picks the code path
+// of a hot command from the entry it already holds in a register, instead of waiting for the staged command's flag word.
+#define NCR_ENTRY_FAST_AFFINE 0x20000000u   // NCR_F_FAST_AFFINE
+#define NCR_ENTRY_SPLIT 0x10000000u         // op == NCR_OP_TEX_SPLIT
+#define NCR_ENTRY_RGB_ONE 0x08000000u       // NCR_F_CT_RGB_ONE
+#define NCR_ENTRY_ALPHA_LT1 0x04000000u     // NCR_F_ALPHA_LT1
+#define NCR_ENTRY_HINTS 0x3c000000u
+#define NCR_ENTRY_INDEX 0x03ffffffu         // 2^26 commands per batch (the recorder submits at 2^20)
 
 struct NcrFrameDims {
     int32_t w, h, ipp;

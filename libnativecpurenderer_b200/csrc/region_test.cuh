@@ -40,7 +40,8 @@ __device__ __forceinline__ NcrQuadRange ncr_quad_range(const double2 m01, const 
 }
 
 // Classifies command `c` (pixel box `box` = l, r, t, b) against BOTH regions of the tile whose top-left pixel is (x0, y0):
-// returns, per region (top in bits 0..2, bottom in bits 3..5), code | covers << 2 where `covers` = the box contains the whole region.
+// returns, per region (top in bits 0..2, bottom in bits 3..5), code | covers << 2 where `covers` = the box contains the whole region,
+// and in the NCR_ENTRY_HINTS bits the command's dispatch hints (the same for both regions).
 // The caller has already established that the box intersects the tile.
 __device__ __forceinline__ uint32_t ncr_region_codes(const NcrCmd* __restrict__ c, const int4 box, int x0, int y0) {
     uint32_t hit[2], covers[2];
@@ -51,7 +52,10 @@ __device__ __forceinline__ uint32_t ncr_region_codes(const NcrCmd* __restrict__ 
         covers[h] = box.x <= x0 && box.y >= x0 + NCR_REGION_W && box.z <= ry0 && box.w >= ry0 + NCR_REGION_H;
     }
     if (!(hit[0] | hit[1])) return 0u;
-    const uint32_t op = __ldg(&c->op);
+    const uint2 of = __ldg((const uint2*)&c->op);   // op, flags
+    const uint32_t op = of.x;
+    const uint32_t hints = ((of.y & NCR_F_FAST_AFFINE) ? NCR_ENTRY_FAST_AFFINE : 0u) | (op == NCR_OP_TEX_SPLIT ? NCR_ENTRY_SPLIT : 0u) |
+                           ((of.y & NCR_F_CT_RGB_ONE) ? NCR_ENTRY_RGB_ONE : 0u) | ((of.y & NCR_F_ALPHA_LT1) ? NCR_ENTRY_ALPHA_LT1 : 0u);
     uint32_t code[2] = {hit[0], hit[1]};
     if (op == NCR_OP_FILL_COLOR || op == NCR_OP_SET_COLOR) {
         // coverage is the box itself (cpp:643-657, 682-691)
@@ -82,5 +86,5 @@ __device__ __forceinline__ uint32_t ncr_region_codes(const NcrCmd* __restrict__ 
             else if (covers[h] && q.x_min >= lo.x && q.x_max <= hi.x && q.y_min >= lo.y && q.y_max <= hi.y) code[h] = 2u;
         }
     }
-    return (code[0] | (code[0] ? covers[0] << 2 : 0u)) | ((code[1] | (code[1] ? covers[1] << 2 : 0u)) << 3);
+    return (code[0] | (code[0] ? covers[0] << 2 : 0u)) | ((code[1] | (code[1] ? covers[1] << 2 : 0u)) << 3) | hints;
 }
