@@ -32,6 +32,9 @@ __device__ __noinline__ double ncr_sqrt(double a) { return __dsqrt_rn(a); }
 #define DIV(a, b) ncr_div((a), (b))
 
 #define FULL 0xffffffffu
+#ifndef NCR_EARLY_SHFL
+#define NCR_EARLY_SHFL 1   // command walk: the shuffle that selects the entry after next is issued before the staging store (see run_region)
+#endif
 #ifndef NCR_USE_COVERS
 #define NCR_USE_COVERS 1   // 0: ignore the entries' "box contains the region" bit (A/B builds)
 #endif
@@ -742,10 +745,19 @@ __device__ __forceinline__ bool run_region(const NcrFlushArgs& A, NcrCmd (*s_cmd
         uint32_t ents_n = ents;
         if (base + 32 < lcount) ents_n = (base + 32 + lane < lcount) ? __ldg(list + loff + base + 32 + lane) : 0u;
         else if (next_valid) ents_n = next_ents;
+#if NCR_EARLY_SHFL
+        // entry of the command after command 1 of this chunk (source lane is taken modulo 32); after the chunk's last command: the
+        // next chunk's / region's first.  Inside the chunk the shuffle for command i + 2 is issued right after command i has been
+        // applied — before the staging store and the warp sync — so its latency is covered by them instead of stalling the fetch
+        // of the next command at the top of the loop.
+        uint32_t nxt = __shfl_sync(FULL, n_here == 1 ? ents_n : ents, n_here == 1 ? 0u : 1u);
+#endif
         for (uint32_t i = 1; i <= n_here; ++i) {
+#if !NCR_EARLY_SHFL
             // command i of this chunk (source lane is taken modulo 32); after the chunk's last one: the next chunk's / region's first
             const bool last = i == n_here;
             const uint32_t nxt = __shfl_sync(FULL, last ? ents_n : ents, last ? 0u : i);
+#endif
             const uint4 pre = __ldg(cmd_words + (size_t)(nxt & NCR_ENTRY_INDEX) * WORDS);   // in flight during the apply
             const NcrCmd& c = s_cmd[0][slot];
 #ifdef NCR_TMA_IDENT
@@ -757,10 +769,17 @@ __device__ __forceinline__ bool run_region(const NcrFlushArgs& A, NcrCmd (*s_cmd
 #endif
             if (!(cur & NCR_ENTRY_INTERIOR) || !apply_interior<ALPHA, COUNT>(c, cur, S, lut, lut_base, dr, dg, db, da, n_applied))
                 apply_cmd<ALPHA, COUNT>(c, A, S, lut, lut_base, dr, dg, db, da, n_applied, NCR_USE_COVERS && (cur & NCR_ENTRY_COVERS) != 0, cur);
+#if NCR_EARLY_SHFL
+            const bool last2 = i + 1 == n_here;
+            const uint32_t nn = __shfl_sync(FULL, last2 ? ents_n : ents, last2 ? 0u : i + 1);   // i == n_here: unused (recomputed above)
+#endif
             slot ^= 1;
             ((uint4*)&s_cmd[0][slot])[cmd_word] = pre;
             __syncwarp();
             cur = nxt;
+#if NCR_EARLY_SHFL
+            nxt = nn;
+#endif
         }
         ents = ents_n;
     }
