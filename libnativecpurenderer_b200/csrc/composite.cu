@@ -35,6 +35,9 @@ __device__ __noinline__ double ncr_sqrt(double a) { return __dsqrt_rn(a); }
 #ifndef NCR_EARLY_SHFL
 #define NCR_EARLY_SHFL 1   // command walk: the shuffle that selects the entry after next is issued before the staging store (see run_region)
 #endif
+#ifndef NCR_PRELOAD_INV
+#define NCR_PRELOAD_INV 1
+#endif
 #ifndef NCR_USE_COVERS
 #define NCR_USE_COVERS 1   // 0: ignore the entries' "box contains the region" bit (A/B builds)
 #endif
@@ -226,6 +229,13 @@ __device__ __forceinline__ bool any_slot(const bool (&in)[NCR_P]) {
     return r;
 }
 
+// The first parameters every inverse-mapped op needs (inv[0..3]), read from the staged command at the top of the command loop —
+// before the fetch of the next command and the dispatch — so that their shared-memory latency is covered by those instead of
+// stalling the first multiply of the map (NCR_PRELOAD_INV=0: read where used, A/B builds).
+struct InvHead {
+    double i0, i1, i2, i3;
+};
+
 // Per-lane pixel slots of the current half-tile.
 struct Slots {
     int xs[NCR_NX], ys[NCR_NY];        // pixel columns / rows owned by this lane
@@ -317,12 +327,12 @@ __device__ __forceinline__ void shade_bilinear_rgba8(const NcrCmd& c, uint32_t l
 // INTERIOR: ncr_bin_fine proved that every pixel of the region passes the box and the four bounds: `in` is constant true, the
 // bounds are not evaluated and every select on coverage folds away.
 template <bool ALPHA, bool COUNT, bool INTERIOR>
-__device__ __forceinline__ void tex_fast(const NcrCmd& c, const uint32_t hint /* the list entry's NCR_ENTRY_* bits */, const Slots& S,
+__device__ __forceinline__ void tex_fast(const NcrCmd& c, const InvHead& ih, const uint32_t hint /* the list entry's NCR_ENTRY_* bits */, const Slots& S,
                                          const double* lut, uint32_t lut_base, bool (&in)[NCR_P], double (&dr)[NCR_P], double (&dg)[NCR_P],
                                          double (&db)[NCR_P], double (&da)[NCR_P], unsigned long long& n_applied) {
     // TransformPointFromMatrix(inv, i, j), cpp:451-452: (inv0*i + inv2*j) + inv4.  inv0*i depends only on the pixel
     // column and inv2*j only on the row: each product is formed once per lane.
-    const double i0 = c.inv[0], i1 = c.inv[1], i2 = c.inv[2], i3 = c.inv[3], i4 = c.inv[4], i5 = c.inv[5];
+    const double i0 = ih.i0, i1 = ih.i1, i2 = ih.i2, i3 = ih.i3, i4 = c.inv[4], i5 = c.inv[5];
     double ax[NCR_NX], bx[NCR_NX], ay[NCR_NY], by[NCR_NY];
 #pragma unroll
     for (int k = 0; k < NCR_NX; ++k) { ax[k] = MUL(i0, S.fx[k]); bx[k] = MUL(i1, S.fx[k]); }
@@ -374,7 +384,7 @@ __device__ __forceinline__ void tex_fast(const NcrCmd& c, const uint32_t hint /*
 // same as in apply_cmd — only `in` is the constant true).  Returns false (warp-uniform) for ops that have no interior
 // variant; the caller then runs apply_cmd, which is always correct.
 template <bool ALPHA, bool COUNT>
-__device__ __forceinline__ bool apply_interior(const NcrCmd& c, const uint32_t hint, const Slots& S, const double* lut, uint32_t lut_base,
+__device__ __forceinline__ bool apply_interior(const NcrCmd& c, const InvHead& ih, const uint32_t hint, const Slots& S, const double* lut, uint32_t lut_base,
                                                double (&dr)[NCR_P], double (&dg)[NCR_P], double (&db)[NCR_P], double (&da)[NCR_P],
                                                unsigned long long& n_applied, const uint32_t* tbox = nullptr, int tbox_at = 0) {
     bool in[NCR_P];
@@ -382,7 +392,7 @@ __device__ __forceinline__ bool apply_interior(const NcrCmd& c, const uint32_t h
     // The hot case is chosen from the list entry (a register), not from the staged command: its parameter loads do not wait for
     // the flag word's shared-memory round trip.
     if (hint & NCR_ENTRY_FAST_AFFINE) {
-        tex_fast<ALPHA, COUNT, true>(c, hint, S, lut, lut_base, in, dr, dg, db, da, n_applied);
+        tex_fast<ALPHA, COUNT, true>(c, ih, hint, S, lut, lut_base, in, dr, dg, db, da, n_applied);
         return true;
     }
     const uint32_t op = c.op, flags = c.flags;
@@ -448,7 +458,7 @@ __device__ __forceinline__ bool apply_interior(const NcrCmd& c, const uint32_t h
 
 // One command applied to the warp's 128 pixels.  `c` lives in shared memory (warp-uniform reads: one wavefront each).
 template <bool ALPHA, bool COUNT>
-__device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A, const Slots& S,
+__device__ __forceinline__ void apply_cmd(const NcrCmd& c, const InvHead& ih, const NcrFlushArgs& A, const Slots& S,
                                           const double* lut, uint32_t lut_base /* lane * 8 */,
                                           double (&dr)[NCR_P], double (&dg)[NCR_P], double (&db)[NCR_P], double (&da)[NCR_P],
                                           unsigned long long& n_applied, const bool covers /* warp-uniform: box contains the region */,
@@ -470,7 +480,7 @@ __device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A
     }
 
     if (hint & NCR_ENTRY_FAST_AFFINE) {   // DrawTexture / DrawSplittedTexture on RGBA8, nearest: the hot case, tested first
-        tex_fast<ALPHA, COUNT, false>(c, hint, S, lut, lut_base, in, dr, dg, db, da, n_applied);
+        tex_fast<ALPHA, COUNT, false>(c, ih, hint, S, lut, lut_base, in, dr, dg, db, da, n_applied);
         return;
     }
     const uint32_t op = c.op, flags = c.flags;
@@ -501,9 +511,9 @@ __device__ __forceinline__ void apply_cmd(const NcrCmd& c, const NcrFlushArgs& A
     if (op != NCR_OP_FILL_COLOR && op != NCR_OP_APPLY_PIXEL && op != NCR_OP_TEX_IDENT && op != NCR_OP_TEX_PERSP) {
         double ax[NCR_NX], bx[NCR_NX], ay[NCR_NY], by[NCR_NY];
 #pragma unroll
-        for (int k = 0; k < NCR_NX; ++k) { ax[k] = MUL(c.inv[0], S.fx[k]); bx[k] = MUL(c.inv[1], S.fx[k]); }
+        for (int k = 0; k < NCR_NX; ++k) { ax[k] = MUL(ih.i0, S.fx[k]); bx[k] = MUL(ih.i1, S.fx[k]); }
 #pragma unroll
-        for (int k = 0; k < NCR_NY; ++k) { ay[k] = MUL(c.inv[2], S.fy[k]); by[k] = MUL(c.inv[3], S.fy[k]); }
+        for (int k = 0; k < NCR_NY; ++k) { ay[k] = MUL(ih.i2, S.fy[k]); by[k] = MUL(ih.i3, S.fy[k]); }
         const double i4 = c.inv[4], i5 = c.inv[5];
         FOR4 {
             X[p] = ADD(ADD(ax[SX(p)], ay[SY(p)]), i4);
@@ -760,15 +770,20 @@ __device__ __forceinline__ bool run_region(const NcrFlushArgs& A, NcrCmd (*s_cmd
 #endif
             const uint4 pre = __ldg(cmd_words + (size_t)(nxt & NCR_ENTRY_INDEX) * WORDS);   // in flight during the apply
             const NcrCmd& c = s_cmd[0][slot];
+#if NCR_PRELOAD_INV
+            const InvHead ih = {c.inv[0], c.inv[1], c.inv[2], c.inv[3]};
+#else
+            const InvHead& ih = *(const InvHead*)&c.inv[0];
+#endif
 #ifdef NCR_TMA_IDENT
             if (tbox && (cur & ~NCR_ENTRY_HINTS) == ((uint32_t)A.tma_cmd | NCR_ENTRY_INTERIOR | NCR_ENTRY_COVERS)) {   // the staged box belongs to this command
                 tma_wait(tbox_mbar, tbox_parity);
                 *tbox_used = true;
-                apply_interior<ALPHA, COUNT>(c, cur, S, lut, lut_base, dr, dg, db, da, n_applied, tbox, ly * NCR_RW + lx);
+                apply_interior<ALPHA, COUNT>(c, ih, cur, S, lut, lut_base, dr, dg, db, da, n_applied, tbox, ly * NCR_RW + lx);
             } else
 #endif
-            if (!(cur & NCR_ENTRY_INTERIOR) || !apply_interior<ALPHA, COUNT>(c, cur, S, lut, lut_base, dr, dg, db, da, n_applied))
-                apply_cmd<ALPHA, COUNT>(c, A, S, lut, lut_base, dr, dg, db, da, n_applied, NCR_USE_COVERS && (cur & NCR_ENTRY_COVERS) != 0, cur);
+            if (!(cur & NCR_ENTRY_INTERIOR) || !apply_interior<ALPHA, COUNT>(c, ih, cur, S, lut, lut_base, dr, dg, db, da, n_applied))
+                apply_cmd<ALPHA, COUNT>(c, ih, A, S, lut, lut_base, dr, dg, db, da, n_applied, NCR_USE_COVERS && (cur & NCR_ENTRY_COVERS) != 0, cur);
 #if NCR_EARLY_SHFL
             const bool last2 = i + 1 == n_here;
             const uint32_t nn = __shfl_sync(FULL, last2 ? ents_n : ents, last2 ? 0u : i + 1);   // i == n_here: unused (recomputed above)
