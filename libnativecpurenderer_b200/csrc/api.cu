@@ -613,7 +613,7 @@ size_t env_limit(const char* name, size_t dflt) {
     return n > 0 ? (size_t)n : dflt;
 }
 const unsigned long long kMaxPendingEntries = env_limit("NCR_MAX_PENDING_ENTRIES", 48ull << 20);   // 4 B each
-const size_t kMaxPendingCmds = env_limit("NCR_MAX_PENDING_CMDS", 1u << 20);
+const size_t kMaxPendingCmds = std::min<size_t>(env_limit("NCR_MAX_PENDING_CMDS", 1u << 20), NCR_ENTRY_INDEX);   // a list entry holds the command index in its low bits
 
 // Starts a command covering the pixel box [l,r) x [t,b) (already clamped to the canvas).  Returns nullptr when
 // the box is empty — no pixel can be touched, so nothing is recorded.
