@@ -170,13 +170,22 @@ __global__ void __launch_bounds__(32 * NCR_FINE_WARPS, NCR_FINE_MIN_CTAS) ncr_bi
     uint32_t n_interior = 0;
     for (int pass = 0; pass < 2; ++pass) {
         uint32_t pos[2] = {0, 0};
+        // candidate indices are loaded one step ahead (clamped, unconditional): the index -> box -> command chain of a step is one
+        // dependent load shorter
+        uint32_t idx_n[NCR_FINE_U];
+#pragma unroll
+        for (int u = 0; u < NCR_FINE_U; ++u) {
+            const uint32_t at = min(u * 32 + lane, ccount - 1);
+            idx_n[u] = direct ? at : A.coarse_list[cbase + at];
+        }
         for (uint32_t k = 0; k < ccount; k += 32 * NCR_FINE_U) {
             uint32_t idx[NCR_FINE_U], code[NCR_FINE_U];
             int4 bxs[NCR_FINE_U];
 #pragma unroll
             for (int u = 0; u < NCR_FINE_U; ++u) {
-                const uint32_t at = min(k + u * 32 + lane, ccount - 1);   // clamped, unconditional
-                idx[u] = direct ? at : A.coarse_list[cbase + at];
+                idx[u] = idx_n[u];
+                const uint32_t at = min(k + 32 * NCR_FINE_U + u * 32 + lane, ccount - 1);
+                idx_n[u] = direct ? at : A.coarse_list[cbase + at];
             }
 #pragma unroll
             for (int u = 0; u < NCR_FINE_U; ++u) bxs[u] = __ldg((const int4*)&A.boxes[idx[u]]);
