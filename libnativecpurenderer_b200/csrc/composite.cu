@@ -10,8 +10,11 @@
 // current one is applied), reads its parameters as warp-uniform LDS broadcasts and amortises them over its 128
 // pixels.  The region's list (written by ncr_bin_fine) holds only commands that can touch the region, each tagged
 // INTERIOR when every pixel of the region provably passes its box and coverage tests: those run straight-line code
-// with no per-pixel test or select on coverage.  Texel fetches of the four pixels are issued back to back before any is consumed.  The write-back produces, in the same pass, the
-// f64 canvas and — when asked — the (iu8)(v*255) image or its YUV 4:2:0 planes (present path).
+// with no per-pixel test or select on coverage.  The entry also carries the command's dispatch hints (fast textured
+// path, split, ct.rgb == 1, a != 1 proven), so the code path of a hot command is chosen from a register before its staged
+// copy is touched.  Texel fetches of the four pixels are issued back to back before any is consumed.  The write-back
+// produces, in the same pass, the f64 canvas (unless the flush is present-only) and — when asked — the (iu8)(v*255) image;
+// its YUV 4:2:0 planes come from ncr_yuv420p right after (present path).
 //
 // Arithmetic: the reference's f64 expression trees (reference src/libNativeCPURenderer.cpp, cited inline),
 // round-to-nearest intrinsics only, no FMA contraction.  Sub-expressions that do not depend on the pixel
