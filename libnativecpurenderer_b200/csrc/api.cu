@@ -603,7 +603,8 @@ bool reserve_cmd(NcrContext* c, size_t extra_aux) {
     return true;
 }
 
-// A batch is submitted early (asynchronously; recording continues in the other staging buffer) once it holds this many
+// A batch is submitted early (recording continues in the other staging buffer while the GPU runs it; the NEXT submit first waits
+// for this one, because the list-size words it reports live in one pinned block per context) once it holds this many
 // commands or tile-list entries.  NCR_MAX_PENDING_CMDS / NCR_MAX_PENDING_ENTRIES override the defaults (tests use tiny
 // values to exercise mid-stream submits).
 size_t env_limit(const char* name, size_t dflt) {
