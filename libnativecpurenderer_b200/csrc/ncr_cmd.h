@@ -82,6 +82,10 @@ struct alignas(16) NcrBox {
 #define NCR_ENTRY_ALPHA_LT1 0x04000000u     // NCR_F_ALPHA_LT1
 #define NCR_ENTRY_HINTS 0x3c000000u
 #define NCR_ENTRY_INDEX 0x03ffffffu         // 2^26 commands per batch (the recorder submits at 2^20)
+static_assert((NCR_ENTRY_INDEX & (NCR_ENTRY_HINTS | NCR_ENTRY_INTERIOR | NCR_ENTRY_COVERS)) == 0 &&
+                  (NCR_ENTRY_INDEX | NCR_ENTRY_HINTS | NCR_ENTRY_INTERIOR | NCR_ENTRY_COVERS) == 0xffffffffu &&
+                  (NCR_ENTRY_FAST_AFFINE | NCR_ENTRY_SPLIT | NCR_ENTRY_RGB_ONE | NCR_ENTRY_ALPHA_LT1) == NCR_ENTRY_HINTS,
+              "list-entry bit fields partition the word");
 
 struct NcrFrameDims {
     int32_t w, h, ipp;
