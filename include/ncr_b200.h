@@ -10,7 +10,8 @@
  *
  * Section 2 is additive (prefix Ncr): batching, pinned host memory, measurement hooks and
  * the extensions BASELINE.json's configs name that the reference does not implement
- * (clip rect, bilinear sampling, polygon fill, perspective quads — "parity unpinned").
+ * (clip rect, polygon fill, perspective quads — "parity unpinned"; bilinear sampling is pinned to the
+ * four-tap code the reference keeps commented out at cpp:575-620).
  */
 #ifndef NCR_B200_H
 #define NCR_B200_H
@@ -159,7 +160,7 @@ double NcrMeasureF64Rate(void);                     /* measured rate of non-fuse
 /* Extensions without a reference implementation (parity unpinned). */
 void NcrSetClipRect(RenderContext* ctx, long x, long y, long width, long height); /* intersects every draw's pixel box */
 void NcrClearClipRect(RenderContext* ctx);
-void NcrSetSampling(RenderContext* ctx, int mode); /* 0 nearest (reference), 1 bilinear (the formula commented out at cpp:575-620) */
+void NcrSetSampling(RenderContext* ctx, int mode); /* 0 nearest (reference), 1 bilinear (the four-tap code commented out at cpp:575-620; bit-identical to it) */
 void NcrFillPolygon(RenderContext* ctx, const double* xy, long n_points, double r, double g, double b, double a); /* cpp:822-845 rule, N points */
 void NcrDrawTexturePerspective(RenderContext* ctx, Texture* tex, const double inv_h[9], double x, double y, double width, double height);
 /* Present path (replaces the f64->u8 loop + sws_scale of PutRendererContextFrame, h:91 cpp:232-256, for

@@ -145,7 +145,9 @@ static void texel(const Image* t, f64 u, f64 v, f64* out) {
     out[3] = t->ipp == 4 ? s[3] : 1.0;
 }
 
-/* extension: the four-tap formula the reference keeps commented out at cpp:575-620 (same clamp as cpp:560-563) */
+/* extension: the four-tap formula the reference keeps commented out at cpp:575-620 (same clamp as cpp:560-563).  PINNED: bit-identical
+ * to the reference translation unit compiled with those lines switched on (Makefile: _ref/libNativeCPURenderer_bilinear.so,
+ * tests/golden/golden_bilinear.json). */
 static void texel_bilinear(const Image* t, f64 u, f64 v, f64* out) {
     if (u < 0) u = 0;
     if (u >= t->w - 1) u = t->w - 2;

@@ -238,6 +238,45 @@ def case_canvas_textures(R, image_rgba):
     return digest(dst)
 
 
+# ---- bilinear sampling (extension X2), pinned to the reference's own commented-out sampler --------------------------------
+# oracle/Makefile builds _ref/libNativeCPURenderer_bilinear.so: the reference translation unit with the four-tap code of
+# cpp:575-620 un-commented.  That build samples bilinearly in EVERY textured draw and has no switch, so the same stream is run
+# with NcrSetSampling(ctx, 1) on the product / restatement (`switch=True`) and without on that build.
+def _bilinear_ctx(R, w, h, alpha, switch):
+    ctx = R.RenderContext(w, h, alpha)
+    if switch:
+        ctx.set_sampling(1)
+    return ctx
+
+
+def make_bilinear_case(which):
+    def run(R, image_rgba, switch=True):
+        if which == "c2_small":
+            ctx = _bilinear_ctx(R, 480, 270, True, switch)
+            streams.stream_c2(ctx, [R.Texture.from_numpy(t) for t in streams.make_c2_textures()], n=600)
+        elif which == "c3_small":
+            ctx = _bilinear_ctx(R, 512, 288, True, switch)
+            streams.stream_c3(ctx, R.Texture.from_numpy(streams.make_atlas(cells=4, cell=64)), n=800, cells=4)
+        elif which == "k1_small":
+            ctx = _bilinear_ctx(R, 640, 360, True, switch)
+            streams.stream_k1(ctx, R.Texture.from_numpy(image_rgba), n=300)
+        else:   # randomised reference-ABI stream (identity and mapped paths, degenerate sizes, RGB and RGBA canvases), three flushes
+            seed = int(which.split("_")[1])
+            w, h, alpha = RANDOM_SHAPES[seed % len(RANDOM_SHAPES)]
+            ctx = _bilinear_ctx(R, w, h, alpha, switch)
+            tex = tiny_textures(R, image_rgba)   # RGBA8, every side >= 2 texels (the reference reads out of bounds below that)
+            for part in range(3):
+                streams.stream_random(ctx, tex, seed * 10 + part, n=70)
+        return digest(ctx)
+
+    return run
+
+
+def bilinear_cases():
+    names = ["c2_small", "c3_small", "k1_small"] + [f"random_{s}" for s in range(10)]
+    return [(n, make_bilinear_case(n)) for n in names]
+
+
 def all_cases(reference_abi_only: bool = False):
     cases = [("k1", case_k1), ("k2", case_k2), ("k3", case_k3), ("k4", case_k4), ("k5", case_k5), ("k6", case_k6),
              ("c2_small", case_c2_small), ("c3_small", case_c3_small), ("c4_small", case_c4_small),

@@ -39,6 +39,24 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_bilinear():
+    """Digests of the reference translation unit with its own commented-out four-tap sampler (cpp:575-620) switched on
+    (oracle/Makefile -> _ref/libNativeCPURenderer_bilinear.so; tests/golden/make_golden.py)."""
+    with open(os.path.join(GOLDEN_DIR, "golden_bilinear.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def ref_bilinear():
+    from libnativecpurenderer_b200.binding import Renderer
+
+    path = os.path.join(os.path.dirname(REF_LIB), "libNativeCPURenderer_bilinear.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libNativeCPURenderer_bilinear.so not built (reference sources absent)")
+    return Renderer(path)
+
+
+@pytest.fixture(scope="session")
 def image_rgba():
     """The reference's test_files/image.png as raw (128,128,4) uint8 (tests/golden/make_golden.py)."""
     return np.load(os.path.join(GOLDEN_DIR, "image_rgba.npz"))["rgba"]

@@ -7,6 +7,8 @@ Run in the build container (needs /root/reference and `make -C oracle ref`):
 Outputs (committed):
   image_rgba.npz   raw RGBA of the reference's test_files/image.png (the only media file on the path)
   golden.json      sha1 of the reference's u8 readback / f64 canvas for the streams in cases.py
+  golden_bilinear.json   the same for cases.bilinear_cases(), from oracle/_ref/libNativeCPURenderer_bilinear.so — the reference
+                   translation unit with its own commented-out four-tap sampler (cpp:575-620) switched on by oracle/Makefile
 
 /root/reference does not exist on the GPU box, so the GPU tests compare against these files.
 """
@@ -40,6 +42,14 @@ def main():
         print(name, out[name])
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
+
+    refb = Renderer(os.path.join(ROOT, "oracle", "_ref", "libNativeCPURenderer_bilinear.so"))
+    outb = {}
+    for name, fn in cases.bilinear_cases():
+        outb[name] = fn(refb, rgba, switch=False)   # that build has no switch: it always samples with four taps
+        print("bilinear", name, outb[name])
+    with open(os.path.join(HERE, "golden_bilinear.json"), "w") as f:
+        json.dump(outb, f, indent=1, sort_keys=True)
 
 
 if __name__ == "__main__":

@@ -37,6 +37,19 @@ def test_port_matches_reference_golden(name, fn, port, golden, image_rgba):
     assert fn(port, image_rgba) == golden[name]
 
 
+@pytest.mark.parametrize("name,fn", cases.bilinear_cases(), ids=lambda v: v if isinstance(v, str) else "")
+def test_port_bilinear_matches_the_references_own_four_tap_sampler(name, fn, port, golden_bilinear, image_rgba):
+    """Extension X2 (NcrSetSampling(ctx, 1)) is PINNED: the restatement with the switch on reproduces, u8 and f64, what the reference
+    translation unit computes once its own commented-out four-tap code (cpp:575-620) is compiled in (that build has no switch)."""
+    assert fn(port, image_rgba, switch=True) == golden_bilinear[name]
+
+
+@pytest.mark.parametrize("seed", range(300, 304))
+def test_port_bilinear_matches_reference_live(seed, port, ref_bilinear, image_rgba):
+    run = cases.make_bilinear_case(f"random_{seed}")
+    assert run(port, image_rgba, switch=True) == run(ref_bilinear, image_rgba, switch=False)
+
+
 @pytest.mark.parametrize("seed", range(200, 206))
 def test_port_matches_reference_live(seed, port, ref, image_rgba):
     run = cases.make_random_case(seed)

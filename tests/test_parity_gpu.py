@@ -249,11 +249,20 @@ def test_c3_full_size_properties(gpu):
     assert hashes[0] == hashes[1]
 
 
-# ---- extensions: no reference implementation exists, so this is product vs this repo's own C restatement only ----------
+# ---- bilinear extension: pinned to the reference's own (commented-out) four-tap sampler ---------------------------------------
+@pytest.mark.parametrize("name,fn", cases.bilinear_cases(), ids=lambda v: v if isinstance(v, str) else "")
+def test_bilinear_matches_the_references_own_four_tap_sampler(name, fn, gpu, golden_bilinear, image_rgba):
+    """NcrSetSampling(ctx, 1) on the CUDA path against digests of the reference translation unit compiled with its commented-out
+    four-tap code (cpp:575-620) switched on: identity and mapped paths, split draws, RGB and RGBA canvases, three flushes."""
+    assert fn(gpu, image_rgba, switch=True) == golden_bilinear[name]
+
+
+# ---- other extensions: no reference implementation exists, so this is product vs this repo's own C restatement only -------
 @pytest.mark.parametrize("seed", range(6))
 def test_extensions_match_port_parity_unpinned(seed, gpu, port, image_rgba):
-    """Clip rect, bilinear sampling, N-gon fill and perspective quads (include/ncr_b200.h §2).  PARITY UNPINNED: the
-    reference has none of these; both sides implement the specs of SURVEY.md §8c.  RGB and RGBA canvases, u8 and f64 textures."""
+    """Clip rect, bilinear sampling, N-gon fill and perspective quads mixed in one stream (include/ncr_b200.h §2).  Clip rect, N-gon
+    fill and perspective are PARITY UNPINNED: the reference has none of them; both sides implement the specs of SURVEY.md §8c
+    (bilinear alone is pinned above).  RGB and RGBA canvases, u8 and f64 textures."""
     w, h, alpha = [(160, 90, True), (97, 61, False), (256, 144, True)][seed % 3]
     got = []
     for R in (gpu, port):
