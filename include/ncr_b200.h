@@ -10,8 +10,10 @@
  *
  * Section 2 is additive (prefix Ncr): batching, pinned host memory, measurement hooks and
  * the extensions BASELINE.json's configs name that the reference does not implement
- * (clip rect, polygon fill, perspective quads — "parity unpinned"; bilinear sampling is pinned to the
- * four-tap code the reference keeps commented out at cpp:575-620).
+ * (clip rect, bilinear sampling, polygon fill — each pinned bit-exactly to reference code, DESIGN.md
+ * section 5: the unmodified reference with outside pixels put back / the four-tap code it keeps commented
+ * out at cpp:575-620 / DrawLine's own pointInPolygon + ApplyPixel loop — and perspective quads, which
+ * have no reference counterpart: "parity unpinned").
  */
 #ifndef NCR_B200_H
 #define NCR_B200_H
@@ -158,10 +160,10 @@ double NcrMeasureD2HRate(unsigned long long bytes_per_copy, int streams, int ite
 double NcrMeasureF64Rate(void);                     /* measured rate of non-fused f64 mul/add instructions per second (roofline aid) */
 
 /* Extensions without a reference implementation (parity unpinned). */
-void NcrSetClipRect(RenderContext* ctx, long x, long y, long width, long height); /* intersects every draw's pixel box */
+void NcrSetClipRect(RenderContext* ctx, long x, long y, long width, long height); /* intersects every draw's pixel box; = the reference drawing unclipped + outside pixels put back */
 void NcrClearClipRect(RenderContext* ctx);
 void NcrSetSampling(RenderContext* ctx, int mode); /* 0 nearest (reference), 1 bilinear (the four-tap code commented out at cpp:575-620; bit-identical to it) */
-void NcrFillPolygon(RenderContext* ctx, const double* xy, long n_points, double r, double g, double b, double a); /* cpp:822-845 rule, N points */
+void NcrFillPolygon(RenderContext* ctx, const double* xy, long n_points, double r, double g, double b, double a); /* DrawLine's loop (cpp:906-916) on N caller points: cpp:822-845 even-odd rule + ApplyPixel */
 void NcrDrawTexturePerspective(RenderContext* ctx, Texture* tex, const double inv_h[9], double x, double y, double width, double height);
 /* Present path (replaces the f64->u8 loop + sws_scale of PutRendererContextFrame, h:91 cpp:232-256, for
  * cap size == canvas size): flush, convert the canvas to the (iu8)(v*255) image and to planar YUV 4:2:0 (BT.601 studio

@@ -372,6 +372,86 @@ def stream_extensions(ctx, textures, seed: int, n: int = 60) -> None:
     ctx.set_sampling(0)
 
 
+def stream_clip(ctx, textures, seed: int, n: int = 70) -> None:
+    """Reference-ABI draws of every kind under clip rects that come and go (tests/cases.py pins the clip extension with it:
+    the unmodified reference, drawing unclipped and having the outside pixels put back, must give the same canvas)."""
+    W, H = ctx.width, ctx.height
+    rng = random.Random(1000 + seed)
+    u = rng.uniform
+    ctx.set_color(.2, .25, .15, 1)
+    for k in range(n):
+        op = rng.random()
+        if op < .12:
+            ctx.set_clip_rect(int(u(-10, W * .7)), int(u(-10, H * .7)), int(u(1, W * .8)), int(u(1, H * .8)))
+            continue
+        if op < .18:
+            ctx.clear_clip_rect()
+            continue
+        ctx.save_state()
+        ctx.translate(u(0, W), u(0, H))
+        if rng.random() < .8:
+            ctx.rotate(u(0, TWO_PI))
+            s = u(.3, 1.5)
+            ctx.scale(s, s)
+        ctx.apply_color_transform(u(.5, 1.1), 1, u(.5, 1), rng.choice([1.0, u(.2, 1)]))
+        if op < .40:
+            tex = rng.choice(textures)
+            ctx.draw_texture(tex, -tex.width / 2, -tex.height / 2, tex.width, tex.height)
+        elif op < .52:
+            tex = rng.choice(textures)
+            ctx.draw_splitted_texture(tex, -30, -20, 60, 40, u(0, .4), u(.5, 1), u(0, .4), u(.5, 1))
+        elif op < .66:
+            ctx.draw_rect(-40, -25, 80, 50, u(0, 1), u(0, 1), u(0, 1), rng.choice([1.0, u(.2, 1)]))
+        elif op < .76:
+            ctx.draw_vertical_grd(-40, -40, 80, 80, u(0, 1), u(0, 1), u(0, 1), u(0, .5), u(0, 1), u(0, 1), u(0, 1), u(.5, 1))
+        elif op < .86:
+            ctx.draw_circle(0, 0, u(8, 45), u(0, 1), u(0, 1), u(0, 1), u(.2, 1))
+        elif op < .95:
+            ctx.draw_line(-50, u(-20, 20), 50, u(-20, 20), u(1, 12), u(0, 1), u(0, 1), u(0, 1), u(.3, 1))
+        else:
+            ctx.fill_color(u(0, 1), u(0, 1), u(0, 1), u(.05, .4))
+        ctx.restore_state()
+    ctx.clear_clip_rect()
+
+
+def stream_polygons(ctx, textures, seed: int, n: int = 60) -> None:
+    """N-gon fills (convex, concave and self-intersecting: the even-odd rule shows) under rotations, scales and colour transforms,
+    mixed with reference-ABI draws (tests/cases.py pins the polygon extension with it)."""
+    W, H = ctx.width, ctx.height
+    rng = random.Random(2000 + seed)
+    u = rng.uniform
+    ctx.set_color(.1, .12, .2, 1)
+    for k in range(n):
+        ctx.save_state()
+        ctx.translate(u(0, W), u(0, H))
+        ctx.rotate(u(0, TWO_PI))
+        s = u(.3, 1.6)
+        ctx.scale(s, s * u(.6, 1.4))
+        ctx.apply_color_transform(u(.5, 1.1), u(.5, 1), 1, rng.choice([1.0, u(.2, 1)]))
+        op = rng.random()
+        if op < .30:     # convex-ish m-gon
+            m = rng.choice([3, 4, 5, 6, 8])
+            pts = [(50 * math.cos(TWO_PI * j / m) * u(.6, 1), 50 * math.sin(TWO_PI * j / m) * u(.6, 1)) for j in range(m)]
+        elif op < .55:   # random points: concave / self-intersecting
+            pts = [(u(-60, 60), u(-60, 60)) for _ in range(rng.choice([3, 5, 7, 9]))]
+        elif op < .65:   # star polygon {5/2}: the pentagon in the middle is OUTSIDE under the even-odd rule
+            pts = [(45 * math.cos(TWO_PI * 2 * j / 5), 45 * math.sin(TWO_PI * 2 * j / 5)) for j in range(5)]
+        elif op < .72:   # degenerate: repeated points, horizontal edges, a point far outside the canvas
+            pts = [(-20, -10), (30, -10), (30, -10), (1e4, 40), (-20, 25)]
+        else:
+            pts = None
+        if pts is not None:
+            ctx.fill_polygon(pts, u(0, 1), u(0, 1), u(0, 1), rng.choice([1.0, u(.2, 1)]))
+        elif op < .86:
+            tex = rng.choice(textures)
+            ctx.draw_texture(tex, -tex.width / 2, -tex.height / 2, tex.width, tex.height)
+        elif op < .94:
+            ctx.draw_line(-50, u(-20, 20), 50, u(-20, 20), u(1, 9), u(0, 1), u(0, 1), u(0, 1), u(.3, 1))
+        else:
+            ctx.draw_rect(-30, -20, 60, 40, u(0, 1), u(0, 1), u(0, 1), u(.2, 1))
+        ctx.restore_state()
+
+
 def stream_c2x(ctx, textures, n: int = 20000, seed: int = 2) -> None:
     """BASELINE config 2 as written, extensions included (product only): the C2 mix with bilinear sampling on half of the
     textured draws, N-gon fills in place of rects, and a clip rect that changes every 500 draws."""

@@ -277,6 +277,80 @@ def bilinear_cases():
     return [(n, make_bilinear_case(n)) for n in names]
 
 
+# ---- clip rect (extension X1), pinned to the UNMODIFIED reference ------------------------------------------------------
+# "A draw under a clip rect touches only the pixels inside it" is expressible with the reference alone: let the reference draw
+# unclipped, then put back every pixel outside the rect (SetPixel stores the four f64 of an RGBA pixel exactly, cpp:494-513).
+class ClipEmulated:
+    """Wraps a context of a library that has no clip rect (the reference build) and gives it one, pixel-exactly."""
+
+    CLIPPED = ("fill_color", "draw_texture", "draw_splitted_texture", "draw_rect", "draw_vertical_grd", "draw_circle", "draw_line")
+
+    def __init__(self, ctx):
+        self._ctx, self._clip = ctx, None
+
+    def set_clip_rect(self, x, y, w, h):
+        W, H = self._ctx.width, self._ctx.height
+        self._clip = (max(0, x), max(0, y), min(W, x + w), min(H, y + h))
+
+    def clear_clip_rect(self):
+        self._clip = None
+
+    def __getattr__(self, name):
+        fn = getattr(self._ctx, name)
+        if name not in self.CLIPPED:
+            return fn
+
+        def clipped(*a, **k):
+            if self._clip is None:
+                return fn(*a, **k)
+            ctx, (l, t, r, b) = self._ctx, self._clip
+            W, H = ctx.width, ctx.height
+            before = ctx.get_buffer_np().reshape(H, W, 4).copy()
+            out = fn(*a, **k)
+            after = ctx.get_buffer_np().reshape(H, W, 4)
+            changed = (before.view(np.uint64) != after.view(np.uint64)).any(axis=2)
+            changed[t:b, l:r] = False   # inside the rect the draw stands
+            for j, i in zip(*np.nonzero(changed)):
+                ctx.set_pixel(int(i), int(j), *before[j, i])
+            return out
+
+        return clipped
+
+
+def make_clip_case(seed):
+    def run(R, image_rgba, native=True):
+        w, h = [(160, 90), (97, 61), (128, 72)][seed % 3]
+        ctx = R.RenderContext(w, h, True)   # RGBA: SetPixel restores a pixel exactly (the 3-channel store spills, cpp:510)
+        tex = tiny_textures(R, image_rgba)
+        streams.stream_clip(ctx if native else ClipEmulated(ctx), tex, seed)
+        return digest(ctx)
+
+    return run
+
+
+def clip_cases():
+    return [(f"clip_{s}", make_clip_case(s)) for s in range(8)]
+
+
+# ---- N-gon fill (extension X3), pinned to the reference's own DrawLine machinery ------------------------------------------
+# oracle/_ref/libNativeCPURenderer_polygon.so = the unmodified reference translation unit + one entry point that runs DrawLine's
+# pixel loop through the reference's own pointInPolygon / ApplyPixel on the caller's points (oracle/ref_polygon_shim.cpp).
+def make_polygon_case(seed):
+    def run(R, image_rgba):
+        # RGBA canvases only: on a 3-channel canvas the reference's SetColor writes 8 bytes past its buffer (cpp:510), which is
+        # harmless often enough for the committed random cases but not in a process that runs this many of them
+        w, h = [(160, 90), (97, 61), (128, 72)][seed % 3]
+        ctx = R.RenderContext(w, h, True)
+        streams.stream_polygons(ctx, tiny_textures(R, image_rgba), seed)
+        return digest(ctx)
+
+    return run
+
+
+def polygon_cases():
+    return [(f"polygon_{s}", make_polygon_case(s)) for s in range(8)]
+
+
 def all_cases(reference_abi_only: bool = False):
     cases = [("k1", case_k1), ("k2", case_k2), ("k3", case_k3), ("k4", case_k4), ("k5", case_k5), ("k6", case_k6),
              ("c2_small", case_c2_small), ("c3_small", case_c3_small), ("c4_small", case_c4_small),

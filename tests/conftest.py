@@ -47,6 +47,30 @@ def golden_bilinear():
 
 
 @pytest.fixture(scope="session")
+def golden_clip():
+    """Digests of the UNMODIFIED reference drawing under an emulated clip rect (cases.ClipEmulated; tests/golden/make_golden.py)."""
+    with open(os.path.join(GOLDEN_DIR, "golden_clip.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def golden_polygon():
+    """Digests of N-gon fills done by the reference's own DrawLine machinery (oracle/ref_polygon_shim.cpp; make_golden.py)."""
+    with open(os.path.join(GOLDEN_DIR, "golden_polygon.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def ref_polygon():
+    from libnativecpurenderer_b200.binding import Renderer
+
+    path = os.path.join(os.path.dirname(REF_LIB), "libNativeCPURenderer_polygon.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libNativeCPURenderer_polygon.so not built (reference sources absent)")
+    return Renderer(path)
+
+
+@pytest.fixture(scope="session")
 def ref_bilinear():
     from libnativecpurenderer_b200.binding import Renderer
 

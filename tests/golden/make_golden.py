@@ -9,6 +9,10 @@ Outputs (committed):
   golden.json      sha1 of the reference's u8 readback / f64 canvas for the streams in cases.py
   golden_bilinear.json   the same for cases.bilinear_cases(), from oracle/_ref/libNativeCPURenderer_bilinear.so — the reference
                    translation unit with its own commented-out four-tap sampler (cpp:575-620) switched on by oracle/Makefile
+  golden_polygon.json  cases.polygon_cases() from oracle/_ref/libNativeCPURenderer_polygon.so: the unmodified reference translation
+                   unit + oracle/ref_polygon_shim.cpp (DrawLine's loop through the reference's own pointInPolygon / ApplyPixel)
+  golden_clip.json  cases.clip_cases(): the UNMODIFIED reference drawing unclipped, with the pixels outside the clip rect put back
+                   after every draw (cases.ClipEmulated) — what the clip-rect extension must reproduce
 
 /root/reference does not exist on the GPU box, so the GPU tests compare against these files.
 """
@@ -50,6 +54,21 @@ def main():
         print("bilinear", name, outb[name])
     with open(os.path.join(HERE, "golden_bilinear.json"), "w") as f:
         json.dump(outb, f, indent=1, sort_keys=True)
+
+    refp = Renderer(os.path.join(ROOT, "oracle", "_ref", "libNativeCPURenderer_polygon.so"))
+    outp = {}
+    for name, fn in cases.polygon_cases():
+        outp[name] = fn(refp, rgba)
+        print("polygon", name, outp[name])
+    with open(os.path.join(HERE, "golden_polygon.json"), "w") as f:
+        json.dump(outp, f, indent=1, sort_keys=True)
+
+    outc = {}
+    for name, fn in cases.clip_cases():
+        outc[name] = fn(ref, rgba, native=False)   # the reference has no clip rect: emulated around its own draws
+        print("clip", name, outc[name])
+    with open(os.path.join(HERE, "golden_clip.json"), "w") as f:
+        json.dump(outc, f, indent=1, sort_keys=True)
 
 
 if __name__ == "__main__":

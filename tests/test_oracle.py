@@ -50,6 +50,34 @@ def test_port_bilinear_matches_reference_live(seed, port, ref_bilinear, image_rg
     assert run(port, image_rgba, switch=True) == run(ref_bilinear, image_rgba, switch=False)
 
 
+@pytest.mark.parametrize("name,fn", cases.polygon_cases(), ids=lambda v: v if isinstance(v, str) else "")
+def test_port_polygon_fill_matches_the_references_drawline_machinery(name, fn, port, golden_polygon, image_rgba):
+    """Extension X3 (NcrFillPolygon) is PINNED: DrawLine (cpp:876-918) is a polygon fill of the stroke's four corners; the same loop
+    run through the reference's own GetInverseTransform / pointInPolygon / ApplyPixel on the caller's points
+    (oracle/ref_polygon_shim.cpp, compiled with the unmodified reference source) gives these digests — convex, concave,
+    self-intersecting (even-odd) and degenerate point sets, under rotations, non-uniform scales and colour transforms."""
+    assert fn(port, image_rgba) == golden_polygon[name]
+
+
+@pytest.mark.parametrize("seed", range(60, 63))
+def test_port_polygon_fill_matches_reference_live(seed, port, ref_polygon, image_rgba):
+    run = cases.make_polygon_case(seed)
+    assert run(port, image_rgba) == run(ref_polygon, image_rgba)
+
+
+@pytest.mark.parametrize("name,fn", cases.clip_cases(), ids=lambda v: v if isinstance(v, str) else "")
+def test_port_clip_rect_matches_the_reference_with_outside_pixels_put_back(name, fn, port, golden_clip, image_rgba):
+    """Extension X1 (NcrSetClipRect) is PINNED: a draw under a clip rect gives the canvas the UNMODIFIED reference gives when it
+    draws unclipped and every pixel outside the rect is put back afterwards (cases.ClipEmulated), u8 and f64, for every draw kind."""
+    assert fn(port, image_rgba, native=True) == golden_clip[name]
+
+
+@pytest.mark.parametrize("seed", range(40, 43))
+def test_port_clip_rect_matches_reference_live(seed, port, ref, image_rgba):
+    run = cases.make_clip_case(seed)
+    assert run(port, image_rgba, native=True) == run(ref, image_rgba, native=False)
+
+
 @pytest.mark.parametrize("seed", range(200, 206))
 def test_port_matches_reference_live(seed, port, ref, image_rgba):
     run = cases.make_random_case(seed)

@@ -257,12 +257,24 @@ def test_bilinear_matches_the_references_own_four_tap_sampler(name, fn, gpu, gol
     assert fn(gpu, image_rgba, switch=True) == golden_bilinear[name]
 
 
-# ---- other extensions: no reference implementation exists, so this is product vs this repo's own C restatement only -------
+# ---- clip-rect extension: pinned to the unmodified reference (draw unclipped, put the outside pixels back) ---------------------
+@pytest.mark.parametrize("name,fn", cases.clip_cases(), ids=lambda v: v if isinstance(v, str) else "")
+def test_clip_rect_matches_the_reference_with_outside_pixels_put_back(name, fn, gpu, golden_clip, image_rgba):
+    assert fn(gpu, image_rgba, native=True) == golden_clip[name]
+
+
+# ---- N-gon fill extension: pinned to the reference's own DrawLine machinery (oracle/ref_polygon_shim.cpp) ---------------------
+@pytest.mark.parametrize("name,fn", cases.polygon_cases(), ids=lambda v: v if isinstance(v, str) else "")
+def test_polygon_fill_matches_the_references_drawline_machinery(name, fn, gpu, golden_polygon, image_rgba):
+    assert fn(gpu, image_rgba) == golden_polygon[name]
+
+
+# ---- all extensions mixed (incl. perspective, which has no reference counterpart): product vs this repo's own C restatement ----
 @pytest.mark.parametrize("seed", range(6))
 def test_extensions_match_port_parity_unpinned(seed, gpu, port, image_rgba):
-    """Clip rect, bilinear sampling, N-gon fill and perspective quads mixed in one stream (include/ncr_b200.h §2).  Clip rect, N-gon
-    fill and perspective are PARITY UNPINNED: the reference has none of them; both sides implement the specs of SURVEY.md §8c
-    (bilinear alone is pinned above).  RGB and RGBA canvases, u8 and f64 textures."""
+    """Clip rect, bilinear sampling, N-gon fill and perspective quads mixed in one stream (include/ncr_b200.h §2).  Perspective quads are
+    PARITY UNPINNED: the reference has nothing like them; both sides implement the spec of SURVEY.md §8c (bilinear, the clip rect and
+    the N-gon fill are each pinned above).  RGB and RGBA canvases, u8 and f64 textures."""
     w, h, alpha = [(160, 90, True), (97, 61, False), (256, 144, True)][seed % 3]
     got = []
     for R in (gpu, port):
