@@ -61,6 +61,14 @@ def golden_polygon():
 
 
 @pytest.fixture(scope="session")
+def golden_apply_pixel():
+    """Digests of the random streams that call ApplyPixel directly, from the reference's own (inline) ApplyPixel exported by the shim
+    build (oracle/ref_polygon_shim.cpp; make_golden.py)."""
+    with open(os.path.join(GOLDEN_DIR, "golden_apply_pixel.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
 def ref_polygon():
     from libnativecpurenderer_b200.binding import Renderer
 

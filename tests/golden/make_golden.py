@@ -11,6 +11,8 @@ Outputs (committed):
                    translation unit with its own commented-out four-tap sampler (cpp:575-620) switched on by oracle/Makefile
   golden_polygon.json  cases.polygon_cases() from oracle/_ref/libNativeCPURenderer_polygon.so: the unmodified reference translation
                    unit + oracle/ref_polygon_shim.cpp (DrawLine's loop through the reference's own pointInPolygon / ApplyPixel)
+  golden_apply_pixel.json   the random streams that call ApplyPixel directly, from the same shim build (it exports the reference's
+                   inline ApplyPixel, cpp:515-549)
   golden_clip.json  cases.clip_cases(): the UNMODIFIED reference drawing unclipped, with the pixels outside the clip rect put back
                    after every draw (cases.ClipEmulated) — what the clip-rect extension must reproduce
 
@@ -62,6 +64,16 @@ def main():
         print("polygon", name, outp[name])
     with open(os.path.join(HERE, "golden_polygon.json"), "w") as f:
         json.dump(outp, f, indent=1, sort_keys=True)
+
+    # ApplyPixel is declared in the reference header (h:109) but defined `inline` (cpp:515), so the plain reference build does not
+    # export it; the shim build does (oracle/ref_polygon_shim.cpp forwards to the reference's own function)
+    outa = {}
+    for name, fn in cases.all_cases(reference_abi_only=False):
+        if name.startswith("random_ap_"):
+            outa[name] = fn(refp, rgba)
+            print("apply_pixel", name, outa[name])
+    with open(os.path.join(HERE, "golden_apply_pixel.json"), "w") as f:
+        json.dump(outa, f, indent=1, sort_keys=True)
 
     outc = {}
     for name, fn in cases.clip_cases():

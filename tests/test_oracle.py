@@ -50,6 +50,13 @@ def test_port_bilinear_matches_reference_live(seed, port, ref_bilinear, image_rg
     assert run(port, image_rgba, switch=True) == run(ref_bilinear, image_rgba, switch=False)
 
 
+@pytest.mark.parametrize("name,fn", [c for c in cases.all_cases() if c[0].startswith("random_ap_")],
+                         ids=lambda v: v if isinstance(v, str) else "")
+def test_port_apply_pixel_matches_the_references_inline_function(name, fn, port, golden_apply_pixel, image_rgba):
+    """ApplyPixel called directly (h:109): the reference defines it `inline` (cpp:515), so only the shim build exports it."""
+    assert fn(port, image_rgba) == golden_apply_pixel[name]
+
+
 @pytest.mark.parametrize("name,fn", cases.polygon_cases(), ids=lambda v: v if isinstance(v, str) else "")
 def test_port_polygon_fill_matches_the_references_drawline_machinery(name, fn, port, golden_polygon, image_rgba):
     """Extension X3 (NcrFillPolygon) is PINNED: DrawLine (cpp:876-918) is a polygon fill of the stroke's four corners; the same loop
