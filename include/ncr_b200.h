@@ -12,8 +12,8 @@
  * the extensions BASELINE.json's configs name that the reference does not implement
  * (clip rect, bilinear sampling, polygon fill — each pinned bit-exactly to reference code, DESIGN.md
  * section 5: the unmodified reference with outside pixels put back / the four-tap code it keeps commented
- * out at cpp:575-620 / DrawLine's own pointInPolygon + ApplyPixel loop — and perspective quads, which
- * have no reference counterpart: "parity unpinned").
+ * out at cpp:575-620 / DrawLine's own pointInPolygon + ApplyPixel loop — and perspective quads, whose
+ * projective map is this repo's spec and whose bounds / sampling / blend are DrawTexture's own).
  */
 #ifndef NCR_B200_H
 #define NCR_B200_H
@@ -159,17 +159,19 @@ double NcrMeasureD2HRate(unsigned long long bytes_per_copy, int streams, int ite
 double NcrMeasureD2HRate(unsigned long long bytes_per_copy, int streams, int iters); /* bytes/s of concurrent device -> pinned-host copies on the default device (readback ceiling aid) */
 double NcrMeasureF64Rate(void);                     /* measured rate of non-fused f64 mul/add instructions per second (roofline aid) */
 
-/* Extensions without a reference implementation (parity unpinned). */
+/* Extensions the reference does not have as entry points; each is pinned to reference code, the perspective
+ * map itself being this repo's spec. */
 void NcrSetClipRect(RenderContext* ctx, long x, long y, long width, long height); /* intersects every draw's pixel box; = the reference drawing unclipped + outside pixels put back */
 void NcrClearClipRect(RenderContext* ctx);
 void NcrSetSampling(RenderContext* ctx, int mode); /* 0 nearest (reference), 1 bilinear (the four-tap code commented out at cpp:575-620; bit-identical to it) */
 void NcrFillPolygon(RenderContext* ctx, const double* xy, long n_points, double r, double g, double b, double a); /* DrawLine's loop (cpp:906-916) on N caller points: cpp:822-845 even-odd rule + ApplyPixel */
-void NcrDrawTexturePerspective(RenderContext* ctx, Texture* tex, const double inv_h[9], double x, double y, double width, double height);
+void NcrDrawTexturePerspective(RenderContext* ctx, Texture* tex, const double inv_h[9], double x, double y, double width, double height); /* rw = 1/(h6 i + h7 j + h8), X = (h0 i + h1 j + h2) rw, Y likewise, hw <= 0 skipped; then DrawTexture's mapped loop, cpp:765-777 */
 /* Present path (replaces the f64->u8 loop + sws_scale of PutRendererContextFrame, h:91 cpp:232-256, for
- * cap size == canvas size): flush, convert the canvas to the (iu8)(v*255) image and to planar YUV 4:2:0 (BT.601 studio
- * swing, 2x2-mean chroma) on the device, and read back only the planes: Y[h][w], U[ch][cw], V[ch][cw] with
- * cw = (w+1)/2, ch = (h+1)/2, contiguous in `out`.  Returns the bytes written (NcrYUV420PSize), -1 on failure.
- * libswscale's exact rounding cannot be checked here (FFmpeg absent): parity unpinned. */
+ * cap size == canvas size): flush, convert the canvas to the (iu8)(v*255) image and to planar YUV 4:2:0 on the device exactly as
+ * libswscale's sws_scale(RGBA|RGB24 -> YUV420P, SWS_BILINEAR) does (BT.601 limited range, pair-sum chroma, {1,3,3,1}/8 vertical
+ * taps), and read back only the planes: Y[h][w], U[ch][cw], V[ch][cw] with cw = (w+1)/2, ch = (h+1)/2,
+ * contiguous in `out`.  Returns the bytes written (NcrYUV420PSize), -1 on failure.  Pinned bit-exactly to libswscale 9.1.100
+ * for even sizes >= 8x8 (tests/golden/make_swscale_fixtures.py). */
 /* n sprites in one call: for k in 0..n-1 { SaveContextState; ApplyTransform(m6[k]) if m6; ApplyColorTransform(ct4[k]) if ct4;
  * DrawSplittedTexture(tex, xywh[k], uv4[k]) if uv4 else DrawTexture(tex, xywh[k]); RestoreContextState } — exactly that call
  * sequence (h:92-93,101,111,115,147), so bit-identical to the loop; m6 is [n][6] (a b c d e f), ct4 [n][4], xywh [n][4],

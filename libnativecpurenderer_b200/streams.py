@@ -452,6 +452,37 @@ def stream_polygons(ctx, textures, seed: int, n: int = 60) -> None:
         ctx.restore_state()
 
 
+def stream_perspective(ctx, textures, seed: int, n: int = 40) -> None:
+    """Perspective-warped quads (mild to strong projective terms, some with the horizon inside the canvas so that hw <= 0 pixels
+    exist) mixed with reference-ABI draws; colour transforms with alpha exactly 1 and below."""
+    W, H = ctx.width, ctx.height
+    rng = random.Random(3000 + seed)
+    u = rng.uniform
+    ctx.set_color(.12, .1, .18, 1)
+    for k in range(n):
+        ctx.save_state()
+        ctx.apply_color_transform(u(.5, 1.1), 1, u(.5, 1), rng.choice([1.0, u(.2, 1)]))
+        op = rng.random()
+        tex = rng.choice(textures)
+        if op < .7:
+            tx_, ty_ = u(0, W), u(0, H)
+            ang = u(0, TWO_PI)
+            c_, s_ = math.cos(ang), math.sin(ang)
+            k_ = u(.5, 2.5)
+            p = rng.choice([1e-3, 4e-3, 2e-2])   # 2e-2: the line hw = 0 crosses a 160-px canvas
+            hinv = (c_ * k_, s_ * k_, -(c_ * k_ * tx_ + s_ * k_ * ty_), -s_ * k_, c_ * k_, (s_ * k_ * tx_ - c_ * k_ * ty_),
+                    u(-p, p), u(-p, p), 1.0)
+            ctx.draw_texture_perspective(tex, hinv, -40, -30, 80, 60)
+        elif op < .85:
+            ctx.translate(u(0, W), u(0, H))
+            ctx.rotate(u(0, TWO_PI))
+            ctx.draw_texture(tex, -tex.width / 2, -tex.height / 2, tex.width, tex.height)
+        else:
+            ctx.translate(u(0, W), u(0, H))
+            ctx.draw_rect(-30, -20, 60, 40, u(0, 1), u(0, 1), u(0, 1), u(.2, 1))
+        ctx.restore_state()
+
+
 def stream_c2x(ctx, textures, n: int = 20000, seed: int = 2) -> None:
     """BASELINE config 2 as written, extensions included (product only): the C2 mix with bilinear sampling on half of the
     textured draws, N-gon fills in place of rects, and a clip rect that changes every 500 draws."""

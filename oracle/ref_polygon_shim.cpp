@@ -33,3 +33,37 @@ extern "C" void NcrFillPolygon(RenderContext* ctx, const double* xy, long n_poin
         }
     }
 }
+
+// Perspective quads (extension X4).  The reference has nothing projective, so the inverse homography is this repo's own spec
+// (include/ncr_b200.h: rw = 1 / (h6*i + h7*j + h8), X = (h0*i + h1*j + h2) * rw, Y likewise, pixels with hw <= 0 skipped); everything
+// AFTER the map is DrawTexture's own mapped loop (cpp:761-777): the four inclusive bounds, the scale to texels and the reference's
+// InterpolateColorFromBuffer and ApplyPixel.
+extern "C" void NcrDrawTexturePerspective(RenderContext* ctx, Texture* tex, const double* h, double x, double y, double width,
+                                          double height) {
+    if (!ctx || !tex || !h) return;
+    if (width == 0 || height == 0) return;   // cpp:726
+    f64 scaleX = tex->width / width;         // cpp:728-729
+    f64 scaleY = tex->height / height;
+    for (i64 i = 0; i < ctx->width; ++i) {
+        for (i64 j = 0; j < ctx->height; ++j) {
+            f64 fi = (f64)i, fj = (f64)j;
+            f64 hw = h[6] * fi + h[7] * fj + h[8];
+            f64 rw = 1.0 / hw;
+            f64 invX = (h[0] * fi + h[1] * fj + h[2]) * rw;
+            f64 invY = (h[3] * fi + h[4] * fj + h[5]) * rw;
+            if (!(hw > 0.0)) continue;
+
+            if (invX < x) continue;   // cpp:765-768
+            if (invX > x + width) continue;
+            if (invY < y) continue;
+            if (invY > y + height) continue;
+
+            f64 u = (invX - x) * scaleX;   // cpp:770-771
+            f64 v = (invY - y) * scaleY;
+
+            f64 r, g, b, a;
+            InterpolateColorFromBuffer(tex->buffer, tex->width, tex->height, tex->enableAlpha, u, v, &r, &g, &b, &a);
+            ApplyPixel(ctx, i, j, r, g, b, a);
+        }
+    }
+}

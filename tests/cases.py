@@ -351,6 +351,21 @@ def polygon_cases():
     return [(f"polygon_{s}", make_polygon_case(s)) for s in range(8)]
 
 
+# ---- perspective quads (extension X4): the projective map is this repo's spec; everything after it is reference code --------
+def make_perspective_case(seed):
+    def run(R, image_rgba):
+        w, h = [(160, 90), (97, 61), (128, 72)][seed % 3]
+        ctx = R.RenderContext(w, h, True)   # RGBA only, see make_polygon_case
+        streams.stream_perspective(ctx, tiny_textures(R, image_rgba), seed)
+        return digest(ctx)
+
+    return run
+
+
+def perspective_cases():
+    return [(f"perspective_{s}", make_perspective_case(s)) for s in range(6)]
+
+
 def all_cases(reference_abi_only: bool = False):
     cases = [("k1", case_k1), ("k2", case_k2), ("k3", case_k3), ("k4", case_k4), ("k5", case_k5), ("k6", case_k6),
              ("c2_small", case_c2_small), ("c3_small", case_c3_small), ("c4_small", case_c4_small),

@@ -61,6 +61,13 @@ def golden_polygon():
 
 
 @pytest.fixture(scope="session")
+def golden_perspective():
+    """Digests of perspective quads from the shim build (spec's projective map + the reference's own bounds / sampler / ApplyPixel)."""
+    with open(os.path.join(GOLDEN_DIR, "golden_perspective.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
 def golden_apply_pixel():
     """Digests of the random streams that call ApplyPixel directly, from the reference's own (inline) ApplyPixel exported by the shim
     build (oracle/ref_polygon_shim.cpp; make_golden.py)."""

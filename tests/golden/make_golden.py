@@ -11,6 +11,8 @@ Outputs (committed):
                    translation unit with its own commented-out four-tap sampler (cpp:575-620) switched on by oracle/Makefile
   golden_polygon.json  cases.polygon_cases() from oracle/_ref/libNativeCPURenderer_polygon.so: the unmodified reference translation
                    unit + oracle/ref_polygon_shim.cpp (DrawLine's loop through the reference's own pointInPolygon / ApplyPixel)
+  golden_perspective.json   cases.perspective_cases() from the same shim build: the projective map is this repo's spec, the bounds /
+                   sampling / blend after it are the reference's own DrawTexture tail (InterpolateColorFromBuffer, ApplyPixel)
   golden_apply_pixel.json   the random streams that call ApplyPixel directly, from the same shim build (it exports the reference's
                    inline ApplyPixel, cpp:515-549)
   golden_clip.json  cases.clip_cases(): the UNMODIFIED reference drawing unclipped, with the pixels outside the clip rect put back
@@ -64,6 +66,13 @@ def main():
         print("polygon", name, outp[name])
     with open(os.path.join(HERE, "golden_polygon.json"), "w") as f:
         json.dump(outp, f, indent=1, sort_keys=True)
+
+    outq = {}
+    for name, fn in cases.perspective_cases():
+        outq[name] = fn(refp, rgba)
+        print("perspective", name, outq[name])
+    with open(os.path.join(HERE, "golden_perspective.json"), "w") as f:
+        json.dump(outq, f, indent=1, sort_keys=True)
 
     # ApplyPixel is declared in the reference header (h:109) but defined `inline` (cpp:515), so the plain reference build does not
     # export it; the shim build does (oracle/ref_polygon_shim.cpp forwards to the reference's own function)

@@ -57,6 +57,15 @@ def test_port_apply_pixel_matches_the_references_inline_function(name, fn, port,
     assert fn(port, image_rgba) == golden_apply_pixel[name]
 
 
+@pytest.mark.parametrize("name,fn", cases.perspective_cases(), ids=lambda v: v if isinstance(v, str) else "")
+def test_port_perspective_quads_match_the_reference_tail_behind_the_spec_map(name, fn, port, golden_perspective, image_rgba):
+    """Extension X4 (NcrDrawTexturePerspective): the reference has nothing projective, so the inverse homography (one reciprocal of the
+    homogeneous w, two multiplies; hw <= 0 skipped) is this repo's spec on both sides — but everything AFTER the map is pinned: the
+    digests come from DrawTexture's own mapped loop (bounds cpp:765-768, scale cpp:770-771, InterpolateColorFromBuffer, ApplyPixel)
+    compiled from the reference source (oracle/ref_polygon_shim.cpp)."""
+    assert fn(port, image_rgba) == golden_perspective[name]
+
+
 @pytest.mark.parametrize("name,fn", cases.polygon_cases(), ids=lambda v: v if isinstance(v, str) else "")
 def test_port_polygon_fill_matches_the_references_drawline_machinery(name, fn, port, golden_polygon, image_rgba):
     """Extension X3 (NcrFillPolygon) is PINNED: DrawLine (cpp:876-918) is a polygon fill of the stroke's four corners; the same loop

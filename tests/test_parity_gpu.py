@@ -273,12 +273,18 @@ def test_polygon_fill_matches_the_references_drawline_machinery(name, fn, gpu, g
     assert fn(gpu, image_rgba) == golden_polygon[name]
 
 
+# ---- perspective quads: spec map + the reference's own DrawTexture tail (oracle/ref_polygon_shim.cpp) ---------------------------
+@pytest.mark.parametrize("name,fn", cases.perspective_cases(), ids=lambda v: v if isinstance(v, str) else "")
+def test_perspective_quads_match_the_reference_tail_behind_the_spec_map(name, fn, gpu, golden_perspective, image_rgba):
+    assert fn(gpu, image_rgba) == golden_perspective[name]
+
+
 # ---- all extensions mixed (incl. perspective, which has no reference counterpart): product vs this repo's own C restatement ----
 @pytest.mark.parametrize("seed", range(6))
 def test_extensions_match_port_parity_unpinned(seed, gpu, port, image_rgba):
-    """Clip rect, bilinear sampling, N-gon fill and perspective quads mixed in one stream (include/ncr_b200.h §2).  Perspective quads are
-    PARITY UNPINNED: the reference has nothing like them; both sides implement the spec of SURVEY.md §8c (bilinear, the clip rect and
-    the N-gon fill are each pinned above).  RGB and RGBA canvases, u8 and f64 textures."""
+    """Clip rect, bilinear sampling, N-gon fill and perspective quads mixed in one stream (include/ncr_b200.h §2).  Each extension is pinned on
+    its own above (the perspective map itself is this repo's spec: the reference has nothing projective); this test mixes them and
+    adds RGB canvases, f64 and 3-channel textures, against the restatement.  RGB and RGBA canvases, u8 and f64 textures."""
     w, h, alpha = [(160, 90, True), (97, 61, False), (256, 144, True)][seed % 3]
     got = []
     for R in (gpu, port):
