@@ -391,7 +391,7 @@ class RenderContext:
         self._lib.NcrFillPolygon(self._ptr, arr, len(flat) // 2, r, g, b, a)
 
     def get_buffer_as_yuv420p(self, out=None):
-        """Present path: planar Y, U, V of the canvas as one uint8 array (parity unpinned, see include/ncr_b200.h)."""
+        """Present path: planar Y, U, V of the canvas as one uint8 array (pinned to libswscale, see include/ncr_b200.h)."""
         import numpy as np
 
         n = self._lib.NcrYUV420PSize(self._ptr)

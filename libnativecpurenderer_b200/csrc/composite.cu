@@ -134,7 +134,7 @@ __device__ __forceinline__ void fetch_any(const void* tex, uint32_t flags, const
     }
 }
 
-// Slow-path sampler: nearest for non-RGBA8 textures, or NCR_F_BILINEAR (extension, parity unpinned): the four-tap
+// Slow-path sampler: nearest for non-RGBA8 textures, or NCR_F_BILINEAR (extension, pinned to the reference's commented-out code): the four-tap
 // formula the reference keeps commented out at cpp:575-620 — same clamp, weights (1-u)(1-v), u(1-v), (1-u)v, uv
 // applied left to right.  Not inlined: it is off the common path and would otherwise be replicated per pixel slot.
 __device__ __noinline__ void sample_slow(const void* tex, uint32_t flags, int w, int h, const double* lut, int l16, double u,
@@ -285,7 +285,7 @@ __device__ __forceinline__ void shade_rgba8(const NcrCmd& c, uint32_t lut_base, 
     }
 }
 
-// Bilinear extension (parity unpinned, cpp:575-620 formula) on RGBA8 textures, written like the nearest path: straight-line
+// Bilinear extension (the cpp:575-620 formula the reference keeps commented out; pinned bit-exactly to it) on RGBA8 textures, written like the nearest path: straight-line
 // over the four pixel slots, the sixteen texel loads issued back to back, decode through the lane-private table.  Performs
 // exactly the operations of sample_slow() + the caller's colour transform and blend, in the same order.
 template <bool ALPHA, bool COUNT>

@@ -22,7 +22,7 @@ enum NcrOp : uint32_t {
     NCR_OP_POLY = 9,         // cpp:876-918 DrawLine's 4-gon / extension: N-gon fill
     NCR_OP_SET_PIXEL = 10,   // cpp:494-513
     NCR_OP_APPLY_PIXEL = 11, // cpp:515-549
-    NCR_OP_TEX_PERSP = 12,   // extension (parity unpinned): projective inverse map
+    NCR_OP_TEX_PERSP = 12,   // extension: projective inverse map (this repo's spec), then DrawTexture's mapped loop
     NCR_OP_COUNT
 };
 
@@ -30,7 +30,7 @@ enum NcrOp : uint32_t {
 enum : uint32_t {
     NCR_F_TEX_ALPHA = 1u << 0,    // texture has 4 channels (else 3; alpha then reads as 1.0)
     NCR_F_TEX_F64 = 1u << 1,      // texels are f64 (else u8 decoded through the k/255.0 table)
-    NCR_F_BILINEAR = 1u << 2,     // extension (parity unpinned): cpp:575-620 formula
+    NCR_F_BILINEAR = 1u << 2,     // extension: the cpp:575-620 four-tap formula (pinned to the reference's commented-out code)
     NCR_F_CLIP = 1u << 3,         // extension: box already intersected with the clip rect on the host
     NCR_F_RGB_SPILL = 1u << 4,    // SetColor on a 3-channel canvas, non-uniform colour: alpha lands in the next element (cpp:510)
     NCR_F_ONLY_RED = 1u << 5,     // SET_PIXEL that writes only the red element (the cpp:510 spill of the previous pixel)

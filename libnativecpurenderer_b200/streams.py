@@ -323,7 +323,7 @@ def stream_random(ctx, textures, seed: int, n: int = 60, use_apply_pixel: bool =
         ctx.restore_state()
 
 
-# --------------------------------------------------------------------------------------------- extensions (parity unpinned)
+# --------------------------------------------------------------------------------------------- extensions (pinned one by one in tests/cases.py)
 def stream_extensions(ctx, textures, seed: int, n: int = 60) -> None:
     """The entry points BASELINE's configs name that the reference does not have (include/ncr_b200.h §2): clip rects,
     bilinear sampling, N-gon fill, perspective quads — mixed with reference-ABI draws.  Product vs C restatement only."""

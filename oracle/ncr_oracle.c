@@ -37,7 +37,7 @@ typedef struct Canvas {
     State st;
     State* stack;
     i64 depth, cap;
-    /* extensions (no reference implementation; PARITY UNPINNED): clip rect and sampling mode */
+    /* extensions (pinned to reference code, see tests/cases.py): clip rect and sampling mode */
     int clip_on;
     i64 cl, cr, ct, cb;
     int bilinear;
@@ -199,7 +199,7 @@ static void raster(Canvas* c, Box bx, const Shader* s) {
     for (i64 j = bx.t; j < bx.b; ++j) {
         for (i64 i = bx.l; i < bx.r; ++i) {
             f64 X, Y, rgba[4];
-            if (s->kind == K_PERSP) {   /* extension (this repo's own spec, parity unpinned): rw = 1 / (h6*i + h7*j + h8);
+            if (s->kind == K_PERSP) {   /* extension (the map is this repo's own spec; the rest is pinned to DrawTexture's loop): rw = 1 / (h6*i + h7*j + h8);
                                          * X = (h0*i + h1*j + h2) * rw, Y = (h3*i + h4*j + h5) * rw — one division per pixel */
                 f64 fi = (f64)i, fj = (f64)j;
                 f64 hw = s->hom[0] * fi + s->hom[1] * fj + s->hom[2];
@@ -539,8 +539,10 @@ Image* CreateMilthmHitEffectTexture(Image* mask, f64 seed, f64 t, f64 r, f64 g, 
 
 long GetVersion(void) { return 1; }
 
-/* ---------------------------------------------------------------- extensions (include/ncr_b200.h section 2; PARITY UNPINNED:
- * the reference implements none of these, so this is only this repository's own second implementation of the same spec) */
+/* ---------------------------------------------------------------- extensions (include/ncr_b200.h section 2).  The reference has none of
+ * these as entry points, but each is PINNED to reference code through the builds of oracle/Makefile (tests/cases.py, DESIGN.md
+ * section 5): clip rect = the unmodified reference + outside pixels put back; bilinear = its own commented-out sampler; polygon fill
+ * = DrawLine's loop; perspective = DrawTexture's mapped loop behind this repo's projective map. */
 void NcrSetClipRect(Canvas* c, long x, long y, long w, long h) {
     c->clip_on = 1;
     c->cl = x < 0 ? 0 : x;
