@@ -264,6 +264,7 @@ def make_bilinear_case(which):
             seed = int(which.split("_")[1])
             w, h, alpha = RANDOM_SHAPES[seed % len(RANDOM_SHAPES)]
             ctx = _bilinear_ctx(R, w, h, alpha, switch)
+            ctx.set_color(0, 0, 0, 0)   # a new canvas is uninitialised heap in the reference (cpp:15) and zero in the product
             tex = tiny_textures(R, image_rgba)   # RGBA8, every side >= 2 texels (the reference reads out of bounds below that)
             for part in range(3):
                 streams.stream_random(ctx, tex, seed * 10 + part, n=70)
@@ -290,7 +291,8 @@ class ClipEmulated:
 
     def set_clip_rect(self, x, y, w, h):
         W, H = self._ctx.width, self._ctx.height
-        self._clip = (max(0, x), max(0, y), min(W, x + w), min(H, y + h))
+        l, t = max(0, x), max(0, y)
+        self._clip = (l, t, max(l, min(W, x + w)), max(t, min(H, y + h)))   # an empty rect stays empty (no negative slice ends)
 
     def clear_clip_rect(self):
         self._clip = None

@@ -5,7 +5,13 @@
 
 Per seed: the randomised reference-ABI stream of tests/cases.py (five canvas shapes, three flushes each, u8 + f64 digests,
 YUV planes) against the C restatement, every 10th seed also against the unmodified reference build (--ref), plus the
-extension stream (clip / bilinear / polygon / perspective; parity unpinned) against the restatement."""
+extension stream (clip / bilinear / polygon / perspective, mixed) against the restatement.
+
+    python tools/fuzz_gpu.py FIRST_SEED COUNT --pins
+
+Per seed: each extension on its own against its reference-derived build (oracle/Makefile): bilinear vs the reference with its
+commented-out sampler switched on, clip rect vs the unmodified reference with the outside pixels put back, N-gon fill and perspective
+quads vs the shim build (DrawLine's / DrawTexture's loops through the reference's own functions)."""
 import os
 import sys
 import time
@@ -21,8 +27,39 @@ from libnativecpurenderer_b200 import streams  # noqa: E402
 from libnativecpurenderer_b200.binding import Renderer  # noqa: E402
 
 
+def pins(first, count):
+    gpu = Renderer()
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    ref = Renderer(os.path.join(ref_dir, "libNativeCPURenderer.so"))
+    refb = Renderer(os.path.join(ref_dir, "libNativeCPURenderer_bilinear.so"))
+    refp = Renderer(os.path.join(ref_dir, "libNativeCPURenderer_polygon.so"))
+    img = np.load(os.path.join(ROOT, "tests", "golden", "image_rgba.npz"))["rgba"]
+    bad, t0 = [], time.time()
+    for seed in range(first, first + count):
+        # RGBA shapes only on the reference side of the bilinear stream: SetColor on a 3-channel canvas overruns its buffer there
+        if cases.RANDOM_SHAPES[seed % len(cases.RANDOM_SHAPES)][2]:
+            run = cases.make_bilinear_case(f"random_{seed}")
+            if run(gpu, img, switch=True) != run(refb, img, switch=False):
+                bad.append(("bilinear", seed))
+        run = cases.make_clip_case(seed)
+        if run(gpu, img, native=True) != run(ref, img, native=False):
+            bad.append(("clip", seed))
+        run = cases.make_polygon_case(seed)
+        if run(gpu, img) != run(refp, img):
+            bad.append(("polygon", seed))
+        run = cases.make_perspective_case(seed)
+        if run(gpu, img) != run(refp, img):
+            bad.append(("perspective", seed))
+        if (seed - first) % 50 == 49:
+            print(f"{seed - first + 1} seeds, {len(bad)} mismatches, {time.time() - t0:.0f} s", flush=True)
+    print(f"DONE pins, seeds {first}..{first + count - 1}: {len(bad)} mismatches {bad[:20]}")
+    return 1 if bad else 0
+
+
 def main():
     first, count = int(sys.argv[1]), int(sys.argv[2])
+    if "--pins" in sys.argv:
+        return pins(first, count)
     use_ref = "--ref" in sys.argv
     gpu = Renderer()
     port = Renderer(os.path.join(ROOT, "oracle", "libncr_oracle.so"))
